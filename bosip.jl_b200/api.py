@@ -1,0 +1,624 @@
+"""Host-side mirror of the BOSIP.jl interface for the batched evaluation path, on top of the C ABI.
+
+Julia is not available in this image, so this module plays the role of the Julia glue (julia/BosipB200.jl): same names,
+argument meaning, shapes and error behaviour as the reference (paths relative to /root/reference):
+
+    NormalLikelihood                               src/likelihoods/normal.jl:16-19
+    BosipProblem                                   src/types/problem.jl:28-35
+    model_posterior -> B200GPPosterior             BOSS.model_posterior / BOSS.ModelPosterior (test/unit/utils.jl:3-11)
+      mean / var / std / mean_and_var / mean_and_std (vector -> length p, matrix d x M -> p x M)
+    log_approx_likelihood / log_likelihood_mean / log_likelihood_variance   src/posterior/likelihood.jl:19-59
+    log_approx_posterior / log_posterior_mean / log_posterior_variance      src/posterior/log_posterior.jl:15-61
+    approx_posterior / posterior_mean / posterior_variance (normalize=...)  src/posterior/posterior.jl:36-145
+    evidence                                       src/posterior/evidence.jl:19-24
+    MaxVar / LogMaxVar                             src/acquisitions/maxvar.jl, logmaxvar.jl
+    B200CandidateAM.maximize_acquisition           BOSS SamplingAM / GridAM (docs/src/hyperparams.md:69)
+    MMDMetric / TVMetric / calculate_metric / calc_mmd / calc_tv            src/metrics/mmd.jl, tv.jl
+
+Every closure has the reference's two methods: a length-d vector -> scalar, a d x M matrix -> length-M vector.
+Matrices use Julia indexing (X[k, i] = coordinate k of point i); NumPy inputs are converted to column-major once,
+torch CUDA tensors are used in place (device pointers) when they are column-major (`X.t().is_contiguous()`)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+SE, MATERN32, MATERN52 = L.SE, L.MATERN32, L.MATERN52
+UNIFORM, NORMAL, TRUNCNORMAL = L.PRIOR_UNIFORM, L.PRIOR_NORMAL, L.PRIOR_TRUNCNORMAL
+
+
+class BosipB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[bosip_b200 {code}] {msg}")
+        self.code = code
+
+
+class DomainError(BosipB200Error, ValueError):
+    """Julia's DomainError from `_assure_nonneg` (src/posterior/likelihood.jl:61-65)."""
+
+
+class PosDefException(BosipB200Error):
+    """Julia's PosDefException from `cholesky`."""
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(L.c_double_p)
+
+
+def _colmajor(x, rows: Optional[int] = None):
+    """Return (keepalive, address, mem, ncols) of a Julia-indexed (rows x n) matrix or length-n vector."""
+    if _is_torch(x):
+        import torch
+        if x.dtype != torch.float64:
+            raise TypeError("device tensors must be float64")
+        if x.dim() == 2:
+            if not x.t().is_contiguous():
+                x = x.t().contiguous().t()
+            n = x.shape[1]
+        else:
+            x = x.contiguous(); n = x.shape[0]
+        if rows is not None and x.dim() == 2 and x.shape[0] != rows:
+            raise ValueError(f"expected {rows} rows, got {x.shape[0]}")
+        mem = L.DEVICE if x.is_cuda else L.HOST
+        return x, x.data_ptr(), mem, n
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 2:
+        if rows is not None and a.shape[0] != rows:
+            raise ValueError(f"expected {rows} rows, got {a.shape[0]}")
+        a = np.asfortranarray(a); n = a.shape[1]
+    else:
+        a = np.ascontiguousarray(a); n = a.shape[0]
+    return a, a.ctypes.data, L.HOST, n
+
+
+def _out(shape, mem, like=None):
+    """Allocate an output in the same memory space as the inputs; 2-D outputs are column-major."""
+    if mem == L.DEVICE:
+        import torch
+        if len(shape) == 2:
+            t = torch.empty((shape[1], shape[0]), dtype=torch.float64, device=like.device).t()
+        else:
+            t = torch.empty(shape, dtype=torch.float64, device=like.device)
+        return t, t.data_ptr()
+    a = np.empty(shape, dtype=np.float64, order="F")
+    return a, a.ctypes.data
+
+
+class Context:
+    """One per (process, GPU).  Raises when the library or a B200 is missing -- there is no CPU path."""
+
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        h = C.c_void_p()
+        rc = self.lib.bosip_b200_init(device, C.byref(h))
+        if rc != 0:
+            raise BosipB200Error(rc, (self.lib.bosip_b200_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def _check(self, rc: int):
+        if rc == 0:
+            return
+        msg = (self.lib.bosip_b200_last_error(self.h) or b"").decode()
+        if rc == L.EDOMAIN:
+            raise DomainError(rc, msg)
+        if rc == L.ENOTPD:
+            raise PosDefException(rc, msg)
+        raise BosipB200Error(rc, msg)
+
+    def set_chunk(self, max_points: int):
+        self._check(self.lib.bosip_b200_set_chunk(self.h, int(max_points)))
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.bosip_b200_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return {"dmma_tflops": a.value, "dfma_tflops": b.value}
+
+    def timing_reset(self, enable: bool = True):
+        self._check(self.lib.bosip_b200_timing_reset(self.h, 1 if enable else 0))
+
+    def timing_get(self):
+        ms = (C.c_double * 3)(); n = (C.c_int64 * 3)()
+        self._check(self.lib.bosip_b200_timing_get(self.h, ms, n))
+        names = ("kstar_mean", "var_gemm", "epilogue")
+        return {k: {"ms": ms[i], "launches": n[i]} for i, k in enumerate(names)}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bosip_b200_shutdown(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        import os
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx
+
+
+# ----------------------------------------------------------------------------------------------- problem pieces
+@dataclass
+class NormalLikelihood:
+    """NormalLikelihood(; z_obs, std_obs) -- src/likelihoods/normal.jl:16-19"""
+    z_obs: np.ndarray
+    std_obs: np.ndarray
+
+    def __post_init__(self):
+        self.z_obs = np.ascontiguousarray(self.z_obs, dtype=np.float64)
+        self.std_obs = np.ascontiguousarray(self.std_obs, dtype=np.float64)
+        if self.z_obs.shape != self.std_obs.shape:
+            raise ValueError("z_obs and std_obs must have the same length")
+
+    def _c(self):
+        return L.LikeNormal(len(self.z_obs), _dptr(self.z_obs), _dptr(self.std_obs))
+
+
+GaussianLikelihood = NormalLikelihood  # src/likelihoods/normal.jl:26
+
+
+@dataclass
+class ProductPrior:
+    """Product of univariate priors: kind[k] in {UNIFORM (a,b), NORMAL (m,s), TRUNCNORMAL (m,s,a,b)}.
+    Stands for the `x_prior::MultivariateDistribution` of BosipProblem (src/types/problem.jl:33) for the priors the
+    reference's examples use; any other prior is passed as precomputed log-pdf values (`logprior=`)."""
+    kind: Sequence[int]
+    params: Sequence[Sequence[float]]
+
+    def __post_init__(self):
+        self.kind = np.ascontiguousarray(self.kind, dtype=np.int32)
+        prm = np.zeros((len(self.kind), 4))
+        for k, q in enumerate(self.params):
+            prm[k, :len(q)] = q
+        self.params = np.ascontiguousarray(prm)
+
+    @property
+    def d(self): return len(self.kind)
+
+    def _c(self, logprior_ptr=None):
+        return L.Prior(self.d, self.kind.ctypes.data_as(L.c_int32_p), _dptr(self.params), logprior_ptr)
+
+    def rand(self, n: int, rng: np.random.Generator) -> np.ndarray:
+        """d x n samples (rand(x_prior, n), src/posterior/evidence.jl:21)."""
+        from scipy.stats import truncnorm
+        out = np.empty((self.d, n))
+        for k in range(self.d):
+            q = self.params[k]
+            if self.kind[k] == UNIFORM:
+                out[k] = rng.uniform(q[0], q[1], n)
+            elif self.kind[k] == NORMAL:
+                out[k] = rng.normal(q[0], q[1], n)
+            else:
+                out[k] = truncnorm.rvs((q[2] - q[0]) / q[1], (q[3] - q[0]) / q[1], loc=q[0], scale=q[1], size=n, random_state=rng)
+        return out
+
+
+@dataclass
+class GaussianProcess:
+    """BOSS.GaussianProcess with fitted (MAP) hyper-parameters: kernel, lambda d x p, alpha p, sigma p
+    (src/subset_problem.jl:38-44).  `mean` is an optional callable X (d x M) -> p x M (prior mean function)."""
+    kernel: int
+    lengthscales: np.ndarray
+    amplitudes: np.ndarray
+    noise_std: np.ndarray
+    mean: Optional[Callable] = None
+    jitter: float = 0.0
+    pred_noise: bool = False
+    clamp_var: bool = True
+
+
+@dataclass
+class BosipProblem:
+    """The fields of BosipProblem the evaluation path reads (src/types/problem.jl:28-35): data, model, likelihood, prior."""
+    X: np.ndarray            # d x N
+    Y: np.ndarray            # p x N
+    model: GaussianProcess
+    likelihood: NormalLikelihood
+    x_prior: ProductPrior
+    bounds: Optional[tuple] = None   # (lb, ub) of the domain
+    ctx: Optional[Context] = None
+    _post: Optional["B200GPPosterior"] = field(default=None, repr=False)
+
+    def model_posterior(self) -> "B200GPPosterior":
+        if self._post is None:
+            self._post = model_posterior(self.model, self.X, self.Y, ctx=self.ctx)
+        return self._post
+
+    def augment(self, x_new: np.ndarray, y_new: np.ndarray):
+        """BOSS.augment_dataset!: append simulations; the cached posterior is dropped."""
+        self.X = np.concatenate([self.X, np.asarray(x_new, float).reshape(self.X.shape[0], -1)], axis=1)
+        self.Y = np.concatenate([self.Y, np.asarray(y_new, float).reshape(self.Y.shape[0], -1)], axis=1)
+        if self._post is not None:
+            self._post.free()
+        self._post = None
+
+
+# ----------------------------------------------------------------------------------------------- ModelPosterior seam
+class B200GPPosterior:
+    """BOSS.ModelPosterior backed by a device handle.  mean/var/... follow test/unit/utils.jl:8-11: vector -> p, matrix -> p x M."""
+
+    def __init__(self, ctx: Context, handle, model: GaussianProcess, d: int, N: int, p: int):
+        self.ctx, self.h, self.model, self.d, self.N, self.p = ctx, handle, model, d, N, p
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.bosip_b200_gp_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def _mean_at(self, X):
+        if self.model.mean is None:
+            return None, None
+        m = np.asfortranarray(np.asarray(self.model.mean(np.asarray(X)), dtype=np.float64).reshape(self.p, -1))
+        return m, m.ctypes.data
+
+    def _predict(self, X, want_mu=True, want_var=True):
+        vec = (np.ndim(X) == 1) if not _is_torch(X) else (X.dim() == 1)
+        Xm = X.reshape(self.d, 1) if vec else X
+        keep, addr, mem, M = _colmajor(Xm, self.d)
+        mkeep, maddr = self._mean_at(Xm) if mem == L.HOST else (None, None)
+        if self.model.mean is not None and mem == L.DEVICE:
+            raise NotImplementedError("a prior mean function needs host inputs")
+        mu, mu_p = _out((self.p, M), mem, keep) if want_mu else (None, None)
+        var, var_p = _out((self.p, M), mem, keep) if want_var else (None, None)
+        self.ctx._check(self.ctx.lib.bosip_b200_gp_predict(self.h, addr, M, mem, maddr, mu_p, var_p))
+        if vec:
+            mu = mu[:, 0] if mu is not None else None
+            var = var[:, 0] if var is not None else None
+        return mu, var
+
+    def mean(self, X): return self._predict(X, True, False)[0]
+    def var(self, X): return self._predict(X, False, True)[1]
+    def std(self, X): return np.sqrt(self.var(X)) if not _is_torch(X) else self.var(X).sqrt()
+    def mean_and_var(self, X): return self._predict(X, True, True)
+
+    def mean_and_std(self, X):
+        mu, var = self._predict(X, True, True)
+        return mu, (np.sqrt(var) if not _is_torch(var) else var.sqrt())
+
+    def factors(self):
+        """(L p x N x N, Linv p x N x N, a N x p) as the device holds them."""
+        Lm = np.empty((self.p, self.N, self.N)); Li = np.empty_like(Lm); a = np.empty((self.p, self.N))
+        self.ctx._check(self.ctx.lib.bosip_b200_gp_get_factors(self.h, _dptr(Lm), _dptr(Li), _dptr(a)))
+        # device layout is column-major per output: transpose the trailing axes to get L[j][r, c]
+        return Lm.transpose(0, 2, 1).copy(), Li.transpose(0, 2, 1).copy(), a.T.copy()
+
+
+def _opts(model: GaussianProcess):
+    return L.GpOpts(float(model.jitter), int(model.pred_noise), int(model.clamp_var))
+
+
+def model_posterior(model: GaussianProcess, X, Y, ctx: Optional[Context] = None) -> B200GPPosterior:
+    """BOSS.model_posterior(problem) -- conditions the GP on the device (src/posterior/log_posterior.jl:81)."""
+    ctx = ctx or default_context()
+    X = np.asfortranarray(np.asarray(X, dtype=np.float64)); Y = np.asfortranarray(np.asarray(Y, dtype=np.float64))
+    d, N = X.shape; p = Y.shape[0]
+    lam = np.asfortranarray(np.asarray(model.lengthscales, dtype=np.float64).reshape(d, p))
+    alpha = np.ascontiguousarray(model.amplitudes, dtype=np.float64); sigma = np.ascontiguousarray(model.noise_std, dtype=np.float64)
+    mX = None
+    if model.mean is not None:
+        mX = np.asfortranarray(np.asarray(model.mean(X), dtype=np.float64).reshape(p, N))
+    h = C.c_void_p(); o = _opts(model)
+    ctx._check(ctx.lib.bosip_b200_gp_fit(ctx.h, model.kernel, d, N, p, _dptr(X), _dptr(Y), _dptr(lam), _dptr(alpha), _dptr(sigma),
+                                         _dptr(mX) if mX is not None else None, C.byref(o), C.byref(h)))
+    return B200GPPosterior(ctx, h, model, d, N, p)
+
+
+def model_posterior_from_factors(model: GaussianProcess, X, L_fac, a, ctx: Optional[Context] = None) -> B200GPPosterior:
+    """Host-factorised variant (exact-parity runs): L_fac[j] lower Cholesky factor of K_j, a N x p."""
+    ctx = ctx or default_context()
+    X = np.asfortranarray(np.asarray(X, dtype=np.float64))
+    d, N = X.shape
+    L_fac = np.asarray(L_fac, dtype=np.float64); p = L_fac.shape[0]
+    Lc = np.ascontiguousarray(L_fac.transpose(0, 2, 1))          # per-output column-major
+    ac = np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)  # N x p column-major == [p][N]
+    lam = np.asfortranarray(np.asarray(model.lengthscales, dtype=np.float64).reshape(d, p))
+    alpha = np.ascontiguousarray(model.amplitudes, dtype=np.float64); sigma = np.ascontiguousarray(model.noise_std, dtype=np.float64)
+    h = C.c_void_p(); o = _opts(model)
+    ctx._check(ctx.lib.bosip_b200_gp_load_factors(ctx.h, model.kernel, d, N, p, _dptr(X), _dptr(lam), _dptr(alpha), _dptr(sigma),
+                                                  _dptr(Lc), _dptr(ac), C.byref(o), C.byref(h)))
+    return B200GPPosterior(ctx, h, model, d, N, p)
+
+
+# ----------------------------------------------------------------------------------------------- fused closures
+def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optional[ProductPrior], X, want: int,
+                   logprior=None):
+    """One fused call: returns dict of the requested length-M outputs + 'n_clamped'."""
+    vec = (np.ndim(X) == 1) if not _is_torch(X) else (X.dim() == 1)
+    Xm = X.reshape(post.d, 1) if vec else X
+    keep, addr, mem, M = _colmajor(Xm, post.d)
+    mkeep, maddr = post._mean_at(Xm) if mem == L.HOST else (None, None)
+    lk = like._c()
+    lp_keep = lp_addr = None
+    if logprior is not None:
+        lp_keep, lp_addr, lp_mem, _ = _colmajor(logprior)
+        if lp_mem != mem:
+            raise ValueError("logprior must live in the same memory space as X")
+    if prior is not None:
+        pr = prior._c(lp_addr)
+    else:
+        pr = L.Prior(post.d, None, None, lp_addr)
+    outs = {}
+    ptrs = []
+    for bit, name in ((L.WANT_APPROX, "log_approx_post"), (L.WANT_MEAN, "log_post_mean"), (L.WANT_VAR, "log_post_var")):
+        if want & bit:
+            o, p_ = _out((M,), mem, keep); outs[name] = o; ptrs.append(p_)
+        else:
+            ptrs.append(None)
+    ncl = C.c_int64(0)
+    post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval(post.h, C.byref(lk), C.byref(pr), addr, M, mem, maddr, want,
+                                                          ptrs[0], ptrs[1], ptrs[2], C.byref(ncl)))
+    if vec:
+        outs = {k: float(v[0]) for k, v in outs.items()}
+    outs["n_clamped"] = ncl.value
+    return outs
+
+
+def _closure(post, like, prior, want, key, transform=None):
+    def f(X, logprior=None):
+        v = posterior_eval(post, like, prior, X, want, logprior)[key]
+        return transform(v) if transform else v
+    return f
+
+
+# likelihood-level closures (no prior): src/posterior/likelihood.jl:19-59
+def log_approx_likelihood(like: NormalLikelihood, post: B200GPPosterior):
+    return _closure(post, like, None, L.WANT_APPROX, "log_approx_post")
+
+
+def log_likelihood_mean(like: NormalLikelihood, post: B200GPPosterior):
+    return _closure(post, like, None, L.WANT_MEAN, "log_post_mean")
+
+
+def log_likelihood_variance(like: NormalLikelihood, post: B200GPPosterior):
+    return _closure(post, like, None, L.WANT_VAR, "log_post_var")
+
+
+# posterior-level closures: src/posterior/log_posterior.jl:15-61
+def log_approx_posterior(bosip: BosipProblem):
+    return _closure(bosip.model_posterior(), bosip.likelihood, bosip.x_prior, L.WANT_APPROX, "log_approx_post")
+
+
+def log_posterior_mean(bosip: BosipProblem):
+    return _closure(bosip.model_posterior(), bosip.likelihood, bosip.x_prior, L.WANT_MEAN, "log_post_mean")
+
+
+def log_posterior_variance(bosip: BosipProblem):
+    return _closure(bosip.model_posterior(), bosip.likelihood, bosip.x_prior, L.WANT_VAR, "log_post_var")
+
+
+def _exp(v):
+    return v.exp() if _is_torch(v) else (math.exp(v) if np.isscalar(v) else np.exp(v))
+
+
+def evidence(bosip: BosipProblem, which: str = "approx", xs=None, samples: int = 10_000, rng=None) -> float:
+    """evidence(post, x_prior; xs, samples) -- src/posterior/evidence.jl:19-24: mean_i post(x_i)/pdf(prior, x_i)."""
+    post = bosip.model_posterior()
+    if xs is None:
+        xs = bosip.x_prior.rand(samples, rng or np.random.default_rng())
+    keep, addr, mem, S = _colmajor(xs, post.d)
+    lk = bosip.likelihood._c(); pr = bosip.x_prior._c()
+    out = C.c_double()
+    w = L.WANT_APPROX if which == "approx" else L.WANT_MEAN
+    post.ctx._check(post.ctx.lib.bosip_b200_evidence_sum(post.h, C.byref(lk), C.byref(pr), addr, S, mem, w, C.byref(out)))
+    return out.value / S
+
+
+def _normalised(bosip, log_f, which, power, normalize, xs, samples):
+    # src/posterior/posterior.jl:36-50, 84-98, 130-145
+    if not normalize:
+        return lambda X, **kw: _exp(log_f(X, **kw))
+    log_py = math.log(evidence(bosip, which, xs, samples))
+    return lambda X, **kw: _exp(log_f(X, **kw) - power * log_py)
+
+
+def approx_posterior(bosip: BosipProblem, normalize=False, xs=None, samples=10_000):
+    return _normalised(bosip, log_approx_posterior(bosip), "approx", 1.0, normalize, xs, samples)
+
+
+def posterior_mean(bosip: BosipProblem, normalize=False, xs=None, samples=10_000):
+    return _normalised(bosip, log_posterior_mean(bosip), "mean", 1.0, normalize, xs, samples)
+
+
+def posterior_variance(bosip: BosipProblem, normalize=False, xs=None, samples=10_000):
+    # normalised variance divides by p(z)^2 with p(z) estimated from the posterior MEAN (posterior.jl:135-138)
+    return _normalised(bosip, log_posterior_variance(bosip), "mean", 2.0, normalize, xs, samples)
+
+
+def approx_likelihood(bosip: BosipProblem):
+    f = log_approx_likelihood(bosip.likelihood, bosip.model_posterior()); return lambda X: _exp(f(X))
+
+
+def likelihood_mean(bosip: BosipProblem):
+    f = log_likelihood_mean(bosip.likelihood, bosip.model_posterior()); return lambda X: _exp(f(X))
+
+
+def likelihood_variance(bosip: BosipProblem):
+    f = log_likelihood_variance(bosip.likelihood, bosip.model_posterior()); return lambda X: _exp(f(X))
+
+
+# ----------------------------------------------------------------------------------------------- acquisitions
+class MaxVar:
+    """src/acquisitions/maxvar.jl:7-11: acq(bosip) = posterior_variance(bosip; normalize=false)"""
+    acq_id = L.ACQ_MAXVAR
+
+    def __call__(self, bosip: BosipProblem, options=None):
+        return posterior_variance(bosip, normalize=False)
+
+
+class LogMaxVar:
+    """src/acquisitions/logmaxvar.jl:11-15: acq(bosip) = log_posterior_variance(bosip)"""
+    acq_id = L.ACQ_LOGMAXVAR
+
+    def __call__(self, bosip: BosipProblem, options=None):
+        return log_posterior_variance(bosip)
+
+
+@dataclass
+class CandidateSource:
+    """points (d x M, host or device) | philox(seed, lb, ub, count) | grid(lb, ub, n_per_dim)"""
+    kind: int
+    points: object = None
+    seed: int = 0
+    lb: Optional[np.ndarray] = None
+    ub: Optional[np.ndarray] = None
+    n_per_dim: int = 0
+    count: int = 0
+
+    @staticmethod
+    def from_points(X): return CandidateSource(L.CAND_POINTS, points=X, count=(X.shape[1]))
+    @staticmethod
+    def philox(seed, lb, ub, count): return CandidateSource(L.CAND_PHILOX, seed=int(seed), lb=np.ascontiguousarray(lb, float), ub=np.ascontiguousarray(ub, float), count=int(count))
+    @staticmethod
+    def grid(lb, ub, n_per_dim):
+        lb = np.ascontiguousarray(lb, float)
+        return CandidateSource(L.CAND_GRID, lb=lb, ub=np.ascontiguousarray(ub, float), n_per_dim=int(n_per_dim), count=int(n_per_dim) ** len(lb))
+
+
+def acq_argmax(post: B200GPPosterior, like, prior, acq, src: CandidateSource, start: int = 0, count: Optional[int] = None):
+    """Fused evaluate + argmax over candidates start..start+count-1 of `src`.  Returns (global index, value, x)."""
+    count = src.count - start if count is None else count
+    cs = L.CandSrc(); cs.kind = src.kind; keep = None
+    if src.kind == L.CAND_POINTS:
+        pts = src.points[:, start:start + count]
+        keep, addr, mem, _ = _colmajor(pts, post.d)
+        cs.points = addr; cs.mem = mem
+    else:
+        cs.seed = src.seed; cs.lb = _dptr(src.lb); cs.ub = _dptr(src.ub); cs.n_per_dim = src.n_per_dim
+    lk = like._c(); pr = prior._c() if prior is not None else L.Prior(post.d, None, None, None)
+    bi, bv = C.c_int64(-1), C.c_double()
+    bx = np.full(post.d, np.nan)
+    post.ctx._check(post.ctx.lib.bosip_b200_acq_argmax(post.h, C.byref(lk), C.byref(pr), C.byref(cs), count, start, acq.acq_id,
+                                                      C.byref(bi), C.byref(bv), _dptr(bx)))
+    return bi.value, bv.value, bx
+
+
+class B200CandidateAM:
+    """BOSS.AcquisitionMaximizer over a candidate set (SamplingAM / GridAM semantics): x* = cand[argmax acq.(cand)],
+    first maximal index on ties.  With torch.distributed initialised the candidate range is sharded across ranks and
+    the per-rank winners are all-gathered (see parallel.py)."""
+
+    def __init__(self, source: CandidateSource):
+        self.source = source
+
+    def maximize_acquisition(self, bosip: BosipProblem, acq):
+        from . import parallel
+        post = bosip.model_posterior()
+        start, count = parallel.shard_range(self.source.count)
+        idx, val, x = acq_argmax(post, bosip.likelihood, bosip.x_prior, acq, self.source, start, count)
+        idx, val, x = parallel.argmax_allgather(idx, val, x)
+        return x, val
+
+
+def candidates(ctx: Context, src: CandidateSource, start: int, count: int, device_out=None) -> np.ndarray:
+    """Materialise PHILOX/GRID candidates (d x count)."""
+    d = len(src.lb)
+    cs = L.CandSrc(); cs.kind = src.kind; cs.seed = src.seed; cs.lb = _dptr(src.lb); cs.ub = _dptr(src.ub); cs.n_per_dim = src.n_per_dim
+    if device_out is not None:
+        ctx._check(ctx.lib.bosip_b200_candidates(ctx.h, C.byref(cs), d, count, start, L.DEVICE, device_out.data_ptr()))
+        return device_out
+    out = np.empty((d, count), order="F")
+    ctx._check(ctx.lib.bosip_b200_candidates(ctx.h, C.byref(cs), d, count, start, L.HOST, out.ctypes.data))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- metrics
+@dataclass
+class Kernel:
+    """KernelFunctions kernel with ARD length-scales: with_lengthscale(kernel, lengthscales) (src/metrics/opt_mmd.jl:39)."""
+    kernel: int
+    lengthscales: np.ndarray
+
+
+def calc_mmd(kernel: Kernel, X, Y, ctx: Optional[Context] = None) -> float:
+    """calc_mmd(kernel, X, Y) -- src/metrics/mmd.jl:23-28; X d x n, Y d x m (columns = samples).
+    With torch.distributed initialised the tile grid is dealt across ranks and the three sums are all-reduced."""
+    from . import parallel
+    ctx = ctx or default_context()
+    lam = np.ascontiguousarray(kernel.lengthscales, dtype=np.float64)
+    d = len(lam)
+    ka, pa, mema, n = _colmajor(X, d)
+    kb, pb, memb, m = _colmajor(Y, d)
+    if mema != memb:
+        raise ValueError("X and Y must live in the same memory space")
+    sums = np.zeros(3)
+    rank, world = parallel.rank_world()
+    ctx._check(ctx.lib.bosip_b200_mmd_sums(ctx.h, kernel.kernel, d, _dptr(lam), pa, n, pb, m, mema, rank, world, _dptr(sums)))
+    sums = parallel.allreduce_sum(sums)
+    return float(sums[0] / (n * n) + sums[1] / (m * m) - 2.0 * sums[2] / (n * m))
+
+
+@dataclass
+class MMDMetric:
+    """src/metrics/mmd.jl:13-15"""
+    kernel: Kernel
+
+
+def _lme(m: float, s: float, G: int) -> float:
+    return m if math.isinf(m) else m + math.log(s) - math.log(G)
+
+
+def calc_tv(log_ws, approx_logvals, true_logvals, ctx: Optional[Context] = None) -> float:
+    """calc_tv(log_ws, approx_logvals, true_logvals) -- src/metrics/tv.jl:59-73.  Each rank passes its slice of the grid
+    when torch.distributed is initialised; the (max, sum) pairs are combined across ranks between the two stages."""
+    from . import parallel
+    ctx = ctx or default_context()
+    kw, pw, mem, G = _colmajor(log_ws); ka, pa, m2, _ = _colmajor(approx_logvals); kt, pt, m3, _ = _colmajor(true_logvals)
+    if not (mem == m2 == m3):
+        raise ValueError("inputs must live in the same memory space")
+    s1 = np.zeros(4)
+    ctx._check(ctx.lib.bosip_b200_tv_stage1(ctx.h, pw, pa, pt, G, mem, _dptr(s1)))
+    (ma, sa), (mt, st_), Gtot = parallel.lse_allgather(s1[0], s1[1]), parallel.lse_allgather(s1[2], s1[3]), parallel.allreduce_count(G)
+    eva, evt = _lme(ma, sa, Gtot), _lme(mt, st_, Gtot)
+    s2 = np.zeros(2)
+    ctx._check(ctx.lib.bosip_b200_tv_stage2(ctx.h, pw, pa, pt, G, mem, eva, evt, _dptr(s2)))
+    md, sd = parallel.lse_allgather(s2[0], s2[1])
+    return 0.5 * math.exp(_lme(md, sd, Gtot))
+
+
+class TVMetric:
+    """TVMetric(; grid, ws | log_ws, true_logpost | true_logvals) -- src/metrics/tv.jl:21-41"""
+
+    def __init__(self, grid, ws=None, log_ws=None, true_logpost=None, true_logvals=None):
+        assert (ws is None) != (log_ws is None)
+        self.grid = np.asfortranarray(np.asarray(grid, float))
+        self.log_ws = np.log(np.asarray(ws, float)) if log_ws is None else np.asarray(log_ws, float)
+        if true_logvals is None and true_logpost is not None:
+            true_logvals = np.asarray(true_logpost(self.grid), float)
+        self.true_logvals = true_logvals
+
+
+def calculate_metric(metric, a, b, ctx: Optional[Context] = None) -> float:
+    """calculate_metric(::MMDMetric, true_samples, approx_samples) (mmd.jl:17-21) /
+       calculate_metric(::TVMetric, true_logpost, approx_logpost) (tv.jl:43-57; closures are called on the whole grid)."""
+    if isinstance(metric, MMDMetric):
+        return calc_mmd(metric.kernel, a, b, ctx)
+    if isinstance(metric, TVMetric):
+        true_logvals = metric.true_logvals if metric.true_logvals is not None else np.asarray(a(metric.grid), float)
+        approx_logvals = np.asarray(b(metric.grid), float)
+        return calc_tv(metric.log_ws, approx_logvals, true_logvals, ctx)
+    raise TypeError(type(metric))

@@ -1,0 +1,595 @@
+// C ABI of libbosip_b200.so (include/bosip_b200.h): context lifecycle, the chunked evaluation pipeline
+// (H2D staging | cross-kernel+mean | variance GEMM | fused epilogue | reductions | D2H), and the entry points.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bosip {
+
+static thread_local std::string g_init_error;
+
+// ------------------------------------------------------------------------------------------------ timing events
+struct EvPair { cudaEvent_t a, b; int kind; };
+struct TimingPool {
+  std::vector<EvPair> pool;
+  size_t used = 0;
+};
+static TimingPool* pool_of(Ctx* ctx);
+
+}  // namespace bosip
+
+struct bosip_b200_ctx {
+  bosip::Ctx c;
+  bosip::TimingPool tp;
+};
+struct bosip_b200_gp {
+  bosip::Gp* g;
+};
+
+namespace bosip {
+
+static TimingPool* pool_of(Ctx* ctx) { return &reinterpret_cast<bosip_b200_ctx*>(ctx)->tp; }
+
+static void t_begin(Ctx* ctx, int kind, cudaStream_t st) {
+  if (!ctx->timing.enabled) return;
+  TimingPool* tp = pool_of(ctx);
+  if (tp->used == tp->pool.size()) {
+    EvPair e; cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.kind = kind;
+    tp->pool.push_back(e);
+  }
+  tp->pool[tp->used].kind = kind;
+  cudaEventRecord(tp->pool[tp->used].a, st);
+}
+static void t_end(Ctx* ctx, cudaStream_t st) {
+  if (!ctx->timing.enabled) return;
+  TimingPool* tp = pool_of(ctx);
+  cudaEventRecord(tp->pool[tp->used].b, st);
+  tp->used++;
+}
+static void t_collect(Ctx* ctx) {  // call after the stream has been synchronised
+  if (!ctx->timing.enabled) return;
+  TimingPool* tp = pool_of(ctx);
+  for (size_t i = 0; i < tp->used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, tp->pool[i].a, tp->pool[i].b) == cudaSuccess) {
+      ctx->timing.ms[tp->pool[i].kind] += ms;
+      ctx->timing.launches[tp->pool[i].kind] += 1;
+    }
+  }
+  tp->used = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+static int ensure_ws(Ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return 0;
+  if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+  BOSIP_CUDA(ctx, cudaMalloc(&ctx->ws, bytes));
+  ctx->ws_bytes = bytes;
+  return 0;
+}
+
+static int make_epi(Ctx* ctx, const Gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior, EpiParams* ep) {
+  memset(ep, 0, sizeof(*ep));
+  ep->p = gp->p; ep->d = gp->d;
+  ep->pred_noise = gp->opts.pred_noise; ep->clamp_var = gp->opts.clamp_var;
+  for (int j = 0; j < gp->p; ++j) { ep->kxx[j] = gp->alpha2[j]; ep->sig2[j] = gp->sig2[j]; ep->z[j] = 0.0; ep->so[j] = 1.0; }
+  if (like) {
+    if (like->p != gp->p) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood dimension p does not match the GP's output dimension");
+    if (!like->z_obs || !like->std_obs) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood needs z_obs and std_obs");
+    double logc = 0.0;
+    for (int j = 0; j < gp->p; ++j) {
+      if (!(like->std_obs[j] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "std_obs must be > 0");
+      ep->z[j] = like->z_obs[j]; ep->so[j] = like->std_obs[j];
+      logc += log(2.0 * sqrt(M_PI) * like->std_obs[j]);  // src/likelihoods/normal.jl:75
+    }
+    ep->log_C = -logc;
+  }
+  ep->has_prior = 0;
+  if (prior) {
+    if (prior->logprior) ep->has_prior = 2;
+    else if (prior->kind) {
+      if (prior->d != gp->d) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "prior dimension d does not match the GP's input dimension");
+      if (!prior->params) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "prior descriptor needs params");
+      ep->has_prior = 1;
+      for (int k = 0; k < gp->d; ++k) {
+        const double* q = prior->params + 4 * k;
+        ep->prior_kind[k] = prior->kind[k];
+        for (int c = 0; c < 4; ++c) ep->prior_prm[k][c] = q[c];
+        switch (prior->kind[k]) {
+          case BOSIP_B200_PRIOR_UNIFORM:
+            if (!(q[1] > q[0])) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "uniform prior needs a < b");
+            ep->prior_const[k] = -log(q[1] - q[0]);
+            break;
+          case BOSIP_B200_PRIOR_NORMAL:
+            if (!(q[1] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "normal prior needs s > 0");
+            break;
+          case BOSIP_B200_PRIOR_TRUNCNORMAL: {
+            if (!(q[1] > 0.0) || !(q[3] > q[2])) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "truncated normal prior needs s > 0 and a < b");
+            // Distributions.Truncated: logtp = log(Phi((b-m)/s) - Phi((a-m)/s))
+            const double tp = 0.5 * erfc(-(q[3] - q[0]) / q[1] * M_SQRT1_2) - 0.5 * erfc(-(q[2] - q[0]) / q[1] * M_SQRT1_2);
+            ep->prior_const[k] = -log(tp);
+            break;
+          }
+          default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown prior kind");
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// What one evaluation sweep does.  Pointers in "user space" follow `mem`.
+struct Sweep {
+  Gp* gp = nullptr;
+  EpiParams ep;
+  bool use_like = false;
+  int mem = BOSIP_B200_HOST;
+  const double* xq = nullptr;                 // d x M (user space) or nullptr with src
+  const bosip_b200_cand_src* src = nullptr;   // generated candidates
+  int64_t M = 0, index_offset = 0;
+  const double* mean_at_xq = nullptr;         // p x M user space
+  const double* logprior = nullptr;           // M user space
+  bool need_var = false;
+  double *mu = nullptr, *var = nullptr, *la = nullptr, *lm = nullptr, *lv = nullptr;  // user-space outputs
+  bool do_argmax = false; int exp_vals = 0;
+  bool do_evidence = false; unsigned evid_which = 0;
+  // results
+  int64_t n_clamped = 0; int64_t domain_idx = -1;
+  double best_val = 0.0; int64_t best_idx = -1; double evid_sum = 0.0;
+};
+
+static int run_sweep(Ctx* ctx, Sweep& sw) {
+  Gp* gp = sw.gp;
+  const int p = gp->p, d = gp->d, Ns = gp->Ns, T = gp->T;
+  const int64_t M = sw.M;
+  if (M < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "M must be >= 0");
+  if (M == 0) return 0;
+  if (!sw.xq && !sw.src) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "query points are required");
+  const bool host = (sw.mem == BOSIP_B200_HOST);
+  const bool gen = (sw.xq == nullptr);
+
+  // ---- n-split of the cross-kernel so that its shared-memory footprint allows >= 4 CTAs per SM
+  int nspan = (int)((56 * 1024) / (8 * (gp->dp + 1))) & ~15;
+  nspan = std::max(16, std::min(nspan, Ns));
+  int nsplit = (Ns + nspan - 1) / nspan;
+  nspan = (int)round_up((Ns + nsplit - 1) / nsplit, 16);
+  nsplit = (Ns + nspan - 1) / nspan;
+
+  // ---- chunk size
+  int64_t mc;
+  if (sw.need_var) {
+    const int64_t by_mem = (int64_t)(3.0e9 / ((double)p * Ns * 8.0)) / TILE_M * TILE_M;
+    mc = std::min<int64_t>((int64_t)ctx->sms * TILE_M * 4, std::max<int64_t>(TILE_M, by_mem));
+  } else {
+    mc = (int64_t)ctx->sms * TILE_M * 16;
+  }
+  if (ctx->user_chunk > 0) mc = std::min(mc, round_up(ctx->user_chunk, TILE_M));
+  mc = std::min(mc, round_up(M, TILE_M));
+  const int64_t nchunks = (M + mc - 1) / mc;
+
+  // ---- workspace carve-up (all sizes in doubles, 256-byte aligned pieces)
+  size_t off = 0;
+  auto carve = [&](size_t n_doubles) { size_t o = off; off += (n_doubles * 8 + 255) / 256 * 256; return o; };
+  const size_t o_Ks = sw.need_var ? carve((size_t)p * Ns * mc) : 0;
+  const size_t o_mu_part = carve((size_t)nsplit * p * mc);
+  const size_t o_q_part = sw.need_var ? carve((size_t)T * p * mc) : 0;
+  const bool stage_x = host || gen;
+  size_t o_x[2] = {0, 0}, o_mean[2] = {0, 0}, o_lpin[2] = {0, 0}, o_mu[2] = {0, 0}, o_var[2] = {0, 0}, o_la[2] = {0, 0},
+         o_lm[2] = {0, 0}, o_lv[2] = {0, 0}, o_lp[2] = {0, 0};
+  const bool want_lv_dev = sw.lv || sw.do_argmax;
+  const bool want_post_dev = sw.do_evidence;
+  for (int b = 0; b < 2; ++b) {
+    if (stage_x) o_x[b] = carve((size_t)d * mc);
+    if (host && sw.mean_at_xq) o_mean[b] = carve((size_t)p * mc);
+    if (host && sw.logprior) o_lpin[b] = carve((size_t)mc);
+    if (host && sw.mu) o_mu[b] = carve((size_t)p * mc);
+    if (host && sw.var) o_var[b] = carve((size_t)p * mc);
+    if ((host && sw.la) || (want_post_dev && sw.evid_which == BOSIP_B200_WANT_APPROX)) o_la[b] = carve((size_t)mc);
+    if ((host && sw.lm) || (want_post_dev && sw.evid_which == BOSIP_B200_WANT_MEAN)) o_lm[b] = carve((size_t)mc);
+    if ((host && sw.lv) || (sw.do_argmax && !sw.lv)) o_lv[b] = carve((size_t)mc);
+    if (want_post_dev) o_lp[b] = carve((size_t)mc);
+  }
+  const size_t o_scr_v = carve(1024), o_scr_i = carve(1024), o_scr_s = carve(256), o_scalars = carve(8);
+  BOSIP_TRY(ensure_ws(ctx, off));
+  char* ws = ctx->ws;
+  auto D = [&](size_t o) { return reinterpret_cast<double*>(ws + o); };
+  double* Ks = sw.need_var ? D(o_Ks) : nullptr;
+  double* mu_part = D(o_mu_part);
+  double* q_part = sw.need_var ? D(o_q_part) : nullptr;
+  // scalars: [0] best_val, [1] best_idx (as long long), [2] evidence accum, [3] n_clamped (ull), [4] domain idx (ull)
+  double* scal = D(o_scalars);
+  {
+    unsigned long long init[8];
+    double zero = 0.0; long long minus1 = -1;
+    memcpy(&init[0], &zero, 8); memcpy(&init[1], &minus1, 8); memcpy(&init[2], &zero, 8);
+    init[3] = 0ull; init[4] = ~0ull; init[5] = init[6] = init[7] = 0ull;
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(scal, init, sizeof(init), cudaMemcpyHostToDevice, ctx->s_comp));
+  }
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(scal + 3);
+
+  cudaStream_t sc = ctx->s_comp, si = ctx->s_in, so = ctx->s_out;
+  (void)want_lv_dev;
+
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = (int)(c & 1);
+    const int64_t c0 = c * mc, mv = std::min(mc, M - c0);
+    const int64_t m_tiles = (mv + TILE_M - 1) / TILE_M, mcu = m_tiles * TILE_M;  // rows actually computed this chunk
+    const double *x_dev, *mean_dev = nullptr, *lpin_dev = nullptr;
+    // ---------------- inputs
+    if (gen) {
+      if (c >= 2) BOSIP_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_out[b], 0));
+      BOSIP_TRY(launch_candidates(ctx, sw.src, d, mv, sw.index_offset + c0, D(o_x[b]), sc));
+      x_dev = D(o_x[b]);
+    } else if (host) {
+      if (c >= 2) BOSIP_CUDA(ctx, cudaStreamWaitEvent(si, ctx->ev_comp[b], 0));  // buffer b's previous consumer is done
+      BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_x[b]), sw.xq + (size_t)c0 * d, (size_t)mv * d * 8, cudaMemcpyHostToDevice, si));
+      if (sw.mean_at_xq) BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_mean[b]), sw.mean_at_xq + (size_t)c0 * p, (size_t)mv * p * 8, cudaMemcpyHostToDevice, si));
+      if (sw.logprior) BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_lpin[b]), sw.logprior + c0, (size_t)mv * 8, cudaMemcpyHostToDevice, si));
+      BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], si));
+      BOSIP_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[b], 0));
+      if (c >= 2) BOSIP_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_out[b], 0));  // output buffer b has been drained
+      x_dev = D(o_x[b]);
+      if (sw.mean_at_xq) mean_dev = D(o_mean[b]);
+      if (sw.logprior) lpin_dev = D(o_lpin[b]);
+    } else {
+      x_dev = sw.xq + (size_t)c0 * d;
+      if (sw.mean_at_xq) mean_dev = sw.mean_at_xq + (size_t)c0 * p;
+      if (sw.logprior) lpin_dev = sw.logprior + c0;
+    }
+    // ---------------- compute
+    t_begin(ctx, 0, sc);
+    BOSIP_TRY(launch_kstar(ctx, gp, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var, sc));
+    t_end(ctx, sc);
+    if (sw.need_var) {
+      t_begin(ctx, 1, sc);
+      BOSIP_TRY(launch_vargemm(ctx, gp, Ks, mc, m_tiles, q_part, sc));
+      t_end(ctx, sc);
+    }
+    (void)mcu;
+    double* mu_o = sw.mu ? (host ? D(o_mu[b]) : sw.mu + (size_t)c0 * p) : nullptr;
+    double* var_o = sw.var ? (host ? D(o_var[b]) : sw.var + (size_t)c0 * p) : nullptr;
+    double* la_o = o_la[b] ? D(o_la[b]) : (sw.la ? sw.la + c0 : nullptr);
+    double* lm_o = o_lm[b] ? D(o_lm[b]) : (sw.lm ? sw.lm + c0 : nullptr);
+    double* lv_o = o_lv[b] ? D(o_lv[b]) : (sw.lv ? sw.lv + c0 : nullptr);
+    double* lp_o = o_lp[b] ? D(o_lp[b]) : nullptr;
+    if (!sw.use_like) { la_o = lm_o = lv_o = lp_o = nullptr; }
+    t_begin(ctx, 2, sc);
+    BOSIP_TRY(launch_epilogue(ctx, gp, sw.ep, x_dev, lpin_dev, mean_dev, mv, mc, nsplit, mu_part, sw.need_var, q_part, mu_o, var_o,
+                              lp_o, la_o, lm_o, lv_o, counters, (uint64_t)c0, sc));
+    if (sw.do_argmax)
+      BOSIP_TRY(launch_argmax_chunk(ctx, lv_o, mv, sw.index_offset + c0, sw.exp_vals, D(o_scr_v), reinterpret_cast<long long*>(D(o_scr_i)),
+                                    scal + 0, reinterpret_cast<long long*>(scal + 1), sc));
+    if (sw.do_evidence)
+      BOSIP_TRY(launch_sum_chunk(ctx, sw.evid_which == BOSIP_B200_WANT_APPROX ? la_o : lm_o, lp_o, mv, D(o_scr_s), scal + 2, sc));
+    t_end(ctx, sc);
+    BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_comp[b], sc));
+    // ---------------- outputs
+    if (host) {
+      BOSIP_CUDA(ctx, cudaStreamWaitEvent(so, ctx->ev_comp[b], 0));
+      if (sw.mu) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.mu + (size_t)c0 * p, D(o_mu[b]), (size_t)mv * p * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.var) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.var + (size_t)c0 * p, D(o_var[b]), (size_t)mv * p * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.la && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.la + c0, D(o_la[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.lm && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.lm + c0, D(o_lm[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.lv && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.lv + c0, D(o_lv[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
+    }
+    BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_out[b], so));
+  }
+  unsigned long long res[8];
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(res, scal, sizeof(res), cudaMemcpyDeviceToHost, sc));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(sc));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(so));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(si));
+  t_collect(ctx);
+  memcpy(&sw.best_val, &res[0], 8);
+  long long bi; memcpy(&bi, &res[1], 8); sw.best_idx = bi;
+  memcpy(&sw.evid_sum, &res[2], 8);
+  sw.n_clamped = (int64_t)res[3];
+  sw.domain_idx = (res[4] == ~0ull) ? -1 : (int64_t)res[4];
+  if (sw.domain_idx >= 0)
+    BOSIP_FAIL(ctx, BOSIP_B200_EDOMAIN,
+               "DomainError: likelihood variance below -1e-8 (src/posterior/likelihood.jl:61-65) at query index " +
+                   std::to_string(sw.domain_idx));
+  return 0;
+}
+
+}  // namespace bosip
+
+using namespace bosip;
+
+#define API_LOCK(ctxp)                        \
+  if (!(ctxp)) return BOSIP_B200_EINVAL;      \
+  Ctx* ctx = &(ctxp)->c;                      \
+  std::lock_guard<std::mutex> lock__(ctx->mu); \
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return BOSIP_B200_ECUDA; }
+
+extern "C" {
+
+int bosip_b200_version(void) { return BOSIP_B200_VERSION; }
+
+const char* bosip_b200_last_error(const bosip_b200_ctx* c) { return c ? c->c.err.c_str() : g_init_error.c_str(); }
+
+int bosip_b200_init(int device, bosip_b200_ctx** out) {
+  if (!out) return BOSIP_B200_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_init_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libbosip_b200 has no CPU path";
+    return BOSIP_B200_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { g_init_error = "device index out of range"; return BOSIP_B200_EINVAL; }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_init_error = std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e);
+    return BOSIP_B200_ECUDA;
+  }
+  if (prop.major != 10) {
+    g_init_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                   "; this library contains sm_100a code only";
+    return BOSIP_B200_ECUDA;
+  }
+  bosip_b200_ctx* h = new bosip_b200_ctx();
+  Ctx* ctx = &h->c;
+  ctx->device = device; ctx->sms = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_comp[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev_t0) == cudaSuccess && cudaEventCreate(&ctx->ev_t1) == cudaSuccess;
+  if (!ok) { g_init_error = "failed to create CUDA streams/events"; delete h; return BOSIP_B200_ECUDA; }
+  *out = h;
+  return 0;
+}
+
+int bosip_b200_shutdown(bosip_b200_ctx* h) {
+  if (!h) return BOSIP_B200_EINVAL;
+  Ctx* ctx = &h->c;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->ws) cudaFree(ctx->ws);
+  for (auto& e : h->tp.pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_in[b]); cudaEventDestroy(ctx->ev_comp[b]); cudaEventDestroy(ctx->ev_out[b]); }
+  cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+  cudaStreamDestroy(ctx->s_comp); cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+  delete h;
+  return 0;
+}
+
+int bosip_b200_set_chunk(bosip_b200_ctx* h, int64_t max_points) {
+  API_LOCK(h);
+  if (max_points < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "chunk must be >= 0");
+  ctx->user_chunk = max_points;
+  return 0;
+}
+
+int bosip_b200_gp_fit(bosip_b200_ctx* h, int kernel_id, int d, int N, int p, const double* X, const double* Y,
+                      const double* lambda, const double* alpha, const double* sigma, const double* mean_at_X,
+                      const bosip_b200_gp_opts* opts, bosip_b200_gp** out) {
+  API_LOCK(h);
+  if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "out is NULL");
+  *out = nullptr;
+  Gp* g = nullptr;
+  BOSIP_TRY(gp_build(ctx, kernel_id, d, N, p, X, Y, lambda, alpha, sigma, mean_at_X, nullptr, nullptr, opts, &g));
+  *out = new bosip_b200_gp{g};
+  return 0;
+}
+
+int bosip_b200_gp_load_factors(bosip_b200_ctx* h, int kernel_id, int d, int N, int p, const double* X, const double* lambda,
+                               const double* alpha, const double* sigma, const double* L, const double* a,
+                               const bosip_b200_gp_opts* opts, bosip_b200_gp** out) {
+  API_LOCK(h);
+  if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!L || !a) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "L and a are required");
+  Gp* g = nullptr;
+  BOSIP_TRY(gp_build(ctx, kernel_id, d, N, p, X, nullptr, lambda, alpha, sigma, nullptr, L, a, opts, &g));
+  *out = new bosip_b200_gp{g};
+  return 0;
+}
+
+int bosip_b200_gp_get_factors(bosip_b200_gp* gh, double* L, double* Linv, double* a) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  Gp* gp = gh->g;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gp->ctx);
+  API_LOCK(h);
+  const size_t nn = (size_t)gp->p * gp->N * gp->N * 8;
+  if (L) BOSIP_CUDA(ctx, cudaMemcpy(L, gp->L, nn, cudaMemcpyDeviceToHost));
+  if (Linv) BOSIP_CUDA(ctx, cudaMemcpy(Linv, gp->Linv, nn, cudaMemcpyDeviceToHost));
+  if (a) BOSIP_CUDA(ctx, cudaMemcpy(a, gp->a, (size_t)gp->p * gp->N * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bosip_b200_gp_free(bosip_b200_gp* gh) {
+  if (!gh) return BOSIP_B200_EINVAL;
+  if (gh->g) {
+    bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+    std::lock_guard<std::mutex> lock(h->c.mu);
+    cudaSetDevice(h->c.device);
+    gp_destroy(gh->g);
+  }
+  delete gh;
+  return 0;
+}
+
+int bosip_b200_gp_predict(bosip_b200_gp* gh, const double* Xq, int64_t M, int mem, const double* mean_at_Xq, double* mu,
+                          double* var) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+  API_LOCK(h);
+  if (!Xq && M > 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "Xq is NULL");
+  if (!mu && !var) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "at least one of mu, var is required");
+  Sweep sw;
+  sw.gp = gh->g; sw.mem = mem; sw.xq = Xq; sw.M = M; sw.mean_at_xq = mean_at_Xq; sw.mu = mu; sw.var = var;
+  sw.need_var = (var != nullptr); sw.use_like = false;
+  BOSIP_TRY(make_epi(ctx, gh->g, nullptr, nullptr, &sw.ep));
+  return run_sweep(ctx, sw);
+}
+
+int bosip_b200_posterior_eval(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                              const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
+                              double* log_approx_post, double* log_post_mean, double* log_post_var, int64_t* n_clamped) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+  API_LOCK(h);
+  if (!like) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood is NULL");
+  if (!Xq && M > 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "Xq is NULL");
+  if ((want & 7u) == 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "`want` selects no output");
+  if (((want & BOSIP_B200_WANT_APPROX) && !log_approx_post) || ((want & BOSIP_B200_WANT_MEAN) && !log_post_mean) ||
+      ((want & BOSIP_B200_WANT_VAR) && !log_post_var))
+    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "an output selected by `want` is NULL");
+  Sweep sw;
+  sw.gp = gh->g; sw.mem = mem; sw.xq = Xq; sw.M = M; sw.mean_at_xq = mean_at_Xq; sw.use_like = true;
+  sw.la = (want & BOSIP_B200_WANT_APPROX) ? log_approx_post : nullptr;
+  sw.lm = (want & BOSIP_B200_WANT_MEAN) ? log_post_mean : nullptr;
+  sw.lv = (want & BOSIP_B200_WANT_VAR) ? log_post_var : nullptr;
+  sw.need_var = (want & (BOSIP_B200_WANT_MEAN | BOSIP_B200_WANT_VAR)) != 0;
+  BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
+  if (prior && prior->logprior) sw.logprior = prior->logprior;
+  int rc = run_sweep(ctx, sw);
+  if (n_clamped) *n_clamped = sw.n_clamped;
+  return rc;
+}
+
+int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                          const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
+                          double* best_val, double* best_x) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+  API_LOCK(h);
+  if (!like || !src || !best_idx || !best_val) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null argument");
+  if (acq != BOSIP_B200_ACQ_MAXVAR && acq != BOSIP_B200_ACQ_LOGMAXVAR) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown acquisition");
+  if (index_offset < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "index_offset must be >= 0");
+  Sweep sw;
+  sw.gp = gh->g; sw.M = M; sw.index_offset = index_offset; sw.use_like = true; sw.need_var = true;
+  sw.do_argmax = true; sw.exp_vals = (acq == BOSIP_B200_ACQ_MAXVAR) ? 1 : 0;
+  bosip_b200_cand_src shifted = *src;
+  if (src->kind == BOSIP_B200_CAND_POINTS) {
+    if (!src->points && M > 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "candidate points are NULL");
+    sw.mem = src->mem; sw.xq = src->points;  // points are this rank's M candidates; index_offset only labels them
+    if (prior && prior->logprior) sw.logprior = prior->logprior;
+  } else if (src->kind == BOSIP_B200_CAND_PHILOX || src->kind == BOSIP_B200_CAND_GRID) {
+    if (src->kind == BOSIP_B200_CAND_GRID && src->n_per_dim < 1) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "n_per_dim must be >= 1");
+    if (prior && prior->logprior) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "host-supplied logprior needs explicit candidate points");
+    sw.mem = BOSIP_B200_DEVICE; sw.xq = nullptr; sw.src = &shifted;
+  } else {
+    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown candidate source kind");
+  }
+  BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
+  BOSIP_TRY(run_sweep(ctx, sw));
+  *best_idx = sw.best_idx;
+  *best_val = sw.best_idx >= 0 ? sw.best_val : -INFINITY;
+  if (best_x && sw.best_idx >= 0) {
+    const int d = gh->g->d;
+    const int64_t local = sw.best_idx - index_offset;
+    if (src->kind == BOSIP_B200_CAND_POINTS) {
+      if (src->mem == BOSIP_B200_HOST) memcpy(best_x, src->points + (size_t)local * d, (size_t)d * 8);
+      else BOSIP_CUDA(ctx, cudaMemcpy(best_x, src->points + (size_t)local * d, (size_t)d * 8, cudaMemcpyDeviceToHost));
+    } else {
+      BOSIP_TRY(ensure_ws(ctx, 4096));
+      BOSIP_TRY(launch_candidates(ctx, src, d, 1, sw.best_idx, reinterpret_cast<double*>(ctx->ws), ctx->s_comp));
+      BOSIP_CUDA(ctx, cudaMemcpyAsync(best_x, ctx->ws, (size_t)d * 8, cudaMemcpyDeviceToHost, ctx->s_comp));
+      BOSIP_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+    }
+  }
+  return 0;
+}
+
+int bosip_b200_candidates(bosip_b200_ctx* h, const bosip_b200_cand_src* src, int d, int64_t M, int64_t index_offset, int mem,
+                          double* out) {
+  API_LOCK(h);
+  if (!src || !out || M < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad arguments");
+  if (src->kind != BOSIP_B200_CAND_PHILOX && src->kind != BOSIP_B200_CAND_GRID) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "source must be PHILOX or GRID");
+  if (M == 0) return 0;
+  if (mem == BOSIP_B200_DEVICE) {
+    BOSIP_TRY(launch_candidates(ctx, src, d, M, index_offset, out, ctx->s_comp));
+  } else {
+    BOSIP_TRY(ensure_ws(ctx, (size_t)M * d * 8));
+    BOSIP_TRY(launch_candidates(ctx, src, d, M, index_offset, reinterpret_cast<double*>(ctx->ws), ctx->s_comp));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(out, ctx->ws, (size_t)M * d * 8, cudaMemcpyDeviceToHost, ctx->s_comp));
+  }
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+  return 0;
+}
+
+int bosip_b200_evidence_sum(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                            const double* xs, int64_t S, int mem, unsigned which, double* sum_out) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+  API_LOCK(h);
+  if (!like || !prior || !xs || !sum_out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null argument");
+  if (which != BOSIP_B200_WANT_APPROX && which != BOSIP_B200_WANT_MEAN) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "which must be WANT_APPROX or WANT_MEAN");
+  Sweep sw;
+  sw.gp = gh->g; sw.mem = mem; sw.xq = xs; sw.M = S; sw.use_like = true;
+  sw.need_var = (which == BOSIP_B200_WANT_MEAN);
+  sw.do_evidence = true; sw.evid_which = which;
+  BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
+  if (prior->logprior) sw.logprior = prior->logprior;
+  BOSIP_TRY(run_sweep(ctx, sw));
+  *sum_out = sw.evid_sum;
+  return 0;
+}
+
+int bosip_b200_mmd_sums(bosip_b200_ctx* h, int kernel_id, int d, const double* lambda, const double* A, int64_t n,
+                        const double* B, int64_t m, int mem, int rank, int world, double* sums_out) {
+  API_LOCK(h);
+  return mmd_sums(ctx, kernel_id, d, lambda, A, n, B, m, mem, rank, world, sums_out);
+}
+
+int bosip_b200_mmd(bosip_b200_ctx* h, int kernel_id, int d, const double* lambda, const double* A, int64_t n, const double* B,
+                   int64_t m, int mem, double* mmd2_out) {
+  API_LOCK(h);
+  if (!mmd2_out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
+  double s[3];
+  BOSIP_TRY(mmd_sums(ctx, kernel_id, d, lambda, A, n, B, m, mem, 0, 1, s));
+  *mmd2_out = s[0] / ((double)n * (double)n) + s[1] / ((double)m * (double)m) - 2.0 * s[2] / ((double)n * (double)m);
+  return 0;
+}
+
+int bosip_b200_tv_stage1(bosip_b200_ctx* h, const double* lw, const double* a, const double* t, int64_t G, int mem, double* out4) {
+  API_LOCK(h);
+  return tv_stage1(ctx, lw, a, t, G, mem, out4);
+}
+int bosip_b200_tv_stage2(bosip_b200_ctx* h, const double* lw, const double* a, const double* t, int64_t G, int mem, double eva,
+                         double evt, double* out2) {
+  API_LOCK(h);
+  return tv_stage2(ctx, lw, a, t, G, mem, eva, evt, out2);
+}
+int bosip_b200_tv(bosip_b200_ctx* h, const double* lw, const double* a, const double* t, int64_t G, int mem, double* tv_out) {
+  API_LOCK(h);
+  if (!tv_out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
+  double s1[4], s2[2];
+  BOSIP_TRY(tv_stage1(ctx, lw, a, t, G, mem, s1));
+  // logmeanexp = logsumexp - log(G); logsumexp returns the max itself when it is infinite (src/utils/utils.jl:9)
+  const double lg = log((double)G);
+  const double eva = isinf(s1[0]) ? s1[0] : s1[0] + log(s1[1]) - lg;
+  const double evt = isinf(s1[2]) ? s1[2] : s1[2] + log(s1[3]) - lg;
+  BOSIP_TRY(tv_stage2(ctx, lw, a, t, G, mem, eva, evt, s2));
+  const double lme = isinf(s2[0]) ? s2[0] : s2[0] + log(s2[1]) - lg;
+  *tv_out = 0.5 * exp(lme);
+  return 0;
+}
+
+int bosip_b200_fp64_peak(bosip_b200_ctx* h, double* dmma, double* dfma) {
+  API_LOCK(h);
+  return fp64_peak(ctx, dmma, dfma);
+}
+
+int bosip_b200_timing_reset(bosip_b200_ctx* h, int enable) {
+  API_LOCK(h);
+  ctx->timing = Timing();
+  ctx->timing.enabled = enable != 0;
+  return 0;
+}
+int bosip_b200_timing_get(bosip_b200_ctx* h, double* ms3, int64_t* launches3) {
+  API_LOCK(h);
+  for (int k = 0; k < 3; ++k) { if (ms3) ms3[k] = ctx->timing.ms[k]; if (launches3) launches3[k] = ctx->timing.launches[k]; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Shared declarations for libbosip_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <mutex>
+#include <string>
+
+#include "../../include/bosip_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libbosip_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace bosip {
+
+// ------------------------------------------------------------------ tiling constants
+constexpr int TILE_M = 128;   // query rows per variance-GEMM CTA tile and per cross-kernel CTA
+constexpr int TILE_N = 128;   // L^{-1} rows (output columns) per variance-GEMM CTA tile
+constexpr int TILE_K = 16;    // k-chunk per pipeline stage; one chunk of one row = 128 B = 4 groups of 4 doubles
+constexpr int MAX_P = 64;     // max output dimensions held in the epilogue parameter block
+constexpr int MAX_D = 32;     // max parameter dimensions
+
+// Element (row, kk) of a [rows][16] chunk is stored at row*16 + swz(row, kk): the four 32-byte groups of a row
+// are XOR-permuted by (row & 3), which makes the m8n8k4 fragment loads (8 rows x 4 consecutive doubles)
+// bank-conflict free without padding, so a whole [128][16] stage is ONE contiguous 16 KB bulk copy.
+__host__ __device__ __forceinline__ int swz(int row, int kk) { return ((((kk >> 2) ^ row) & 3) << 2) | (kk & 3); }
+
+struct Ctx;
+
+// Parameters of the fused epilogue (likelihood + prior), passed by value to kernels.
+struct EpiParams {
+  int p, d;
+  int has_prior;            // 0: none, 1: descriptor, 2: logprior array
+  int pred_noise, clamp_var;
+  double z[MAX_P], so[MAX_P], kxx[MAX_P], sig2[MAX_P];
+  double log_C;             // -sum log(2 sqrt(pi) so_j)      (src/likelihoods/normal.jl:75)
+  int prior_kind[MAX_D];
+  double prior_prm[MAX_D][4];
+  double prior_const[MAX_D];  // per-dimension additive constant (uniform: -log(b-a); truncnormal: -logtp)
+};
+
+// A conditioned GP on the device.
+struct Gp {
+  Ctx* ctx;
+  int kernel_id, d, dp, N, Ns, p, T, KC;
+  bosip_b200_gp_opts opts;
+  double* Us = nullptr;     // [p][dp][Ns]  training inputs scaled by c_kernel / lambda_j (SoA, zero padded)
+  double* scale = nullptr;  // [p][dp]      c_kernel / lambda_jk (0 for padded dims)
+  double* As = nullptr;     // [p][Ns]      alpha_j^2 * a_j (zero padded)
+  double* LinvT = nullptr;  // [p][T][KC][128][16] alpha_j^2 * L_j^{-1}, tile-major + swizzled (see swz)
+  double* L = nullptr;      // [p][N][N] col-major lower Cholesky factor (kept for gp_get_factors)
+  double* Linv = nullptr;   // [p][N][N] col-major L^{-1}
+  double* a = nullptr;      // [p][N]
+  double alpha2[MAX_P], sig2[MAX_P];
+};
+
+struct Timing {
+  bool enabled = false;
+  double ms[3] = {0, 0, 0};
+  int64_t launches[3] = {0, 0, 0};
+};
+
+struct Ctx {
+  int device = 0;
+  int sms = 0;
+  std::mutex mu;
+  std::string err;
+  cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+  int64_t user_chunk = 0;
+  // chunk workspace (grown on demand)
+  size_t ws_bytes = 0;
+  char* ws = nullptr;
+  Timing timing;
+};
+
+#define BOSIP_CUDA(ctx, call)                                                                          \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +       \
+                   std::to_string(__LINE__) + ")";                                                     \
+      return (e__ == cudaErrorMemoryAllocation) ? BOSIP_B200_ENOMEM : BOSIP_B200_ECUDA;                \
+    }                                                                                                  \
+  } while (0)
+
+#define BOSIP_FAIL(ctx, code, msg) \
+  do {                             \
+    (ctx)->err = (msg);            \
+    return (code);                 \
+  } while (0)
+
+#define BOSIP_TRY(expr)          \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int pad_dim(int d) {
+  const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 24, 32};
+  for (int o : opts) if (d <= o) return o;
+  return -1;
+}
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif
+
+// ------------------------------------------------------------------ cross-TU host entry points
+// kstar.cu
+int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit,
+                 int nspan, double* Ks, double* mu_part, bool write_k, cudaStream_t st);
+// vargemm.cu
+int launch_vargemm(Ctx* ctx, const Gp* gp, const double* Ks, int64_t mc, int64_t m_tiles, double* q_part, cudaStream_t st);
+// epilogue.cu
+int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* xq, const double* logprior,
+                    const double* mean_at_xq, int64_t m_valid, int64_t mc, int nsplit, const double* mu_part,
+                    bool have_var, const double* q_part, double* mu_out, double* var_out, double* lp_out,
+                    double* log_approx, double* log_mean, double* log_var, unsigned long long* counters,
+                    uint64_t index_base, cudaStream_t st);
+int launch_argmax_chunk(Ctx* ctx, const double* vals, int64_t m_valid, int64_t global_offset, int exp_vals,
+                        double* scratch_val, long long* scratch_idx, double* best_val, long long* best_idx,
+                        cudaStream_t st);
+int launch_sum_chunk(Ctx* ctx, const double* log_post, const double* log_prior, int64_t m_valid, double* scratch,
+                     double* accum, cudaStream_t st);
+int launch_candidates(Ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t m, int64_t offset, double* out,
+                      cudaStream_t st);
+// fit.cu
+int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, const double* Y, const double* lambda,
+             const double* alpha, const double* sigma, const double* mean_at_X, const double* L_host,
+             const double* a_host, const bosip_b200_gp_opts* opts, Gp** out);
+void gp_destroy(Gp* gp);
+// metrics.cu
+int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double* A, int64_t n, const double* B,
+             int64_t m, int mem, int rank, int world, double* sums);
+int tv_stage1(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* out4);
+int tv_stage2(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double eva,
+              double evt, double* out2);
+// peaks.cu
+int fp64_peak(Ctx* ctx, double* dmma, double* dfma);
+
+}  // namespace bosip

@@ -1,0 +1,261 @@
+// Fused epilogue: GP (mu, sigma^2) assembly + NormalLikelihood algebra + log-prior + posterior closures, and the
+// block reductions that follow them (acquisition argmax, evidence sum), and device-side candidate generation.
+//
+// Reference statements restated here (paths relative to /root/reference):
+//   normlogpdf                      Distributions.logpdf(Normal) = StatsFuns.normlogpdf           
+//   plug-in log-likelihood          src/likelihoods/normal.jl:28-30 via src/posterior/likelihood.jl:19-29
+//   log E[l]                        src/likelihoods/normal.jl:42-51 + src/posterior/likelihood.jl:34-43
+//   log E[l^2]                      src/likelihoods/normal.jl:67-77
+//   log V[l], clamp, DomainError    src/posterior/likelihood.jl:47-65
+//   log-prior                       src/posterior/log_posterior.jl:228-229
+//   log_approx_posterior / log_posterior_mean / log_posterior_variance   src/posterior/log_posterior.jl:15-61
+#include <float.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace bosip {
+
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+constexpr double MAX_NEG_VAR = 1e-8;  // src/posterior/likelihood.jl:3
+
+__device__ __forceinline__ double normlogpdf(double mu, double s, double z) {
+  const double zv = (z - mu) / s;
+  return -(zv * zv + LOG2PI) / 2.0 - log(s);
+}
+
+__device__ __forceinline__ double log_prior_point(const EpiParams& ep, const double* __restrict__ x) {
+  double lp = 0.0;
+  for (int k = 0; k < ep.d; ++k) {
+    const double xk = x[k];
+    const int kind = ep.prior_kind[k];
+    if (kind == BOSIP_B200_PRIOR_UNIFORM) {
+      lp += (xk >= ep.prior_prm[k][0] && xk <= ep.prior_prm[k][1]) ? ep.prior_const[k] : -INFINITY;
+    } else if (kind == BOSIP_B200_PRIOR_NORMAL) {
+      lp += normlogpdf(ep.prior_prm[k][0], ep.prior_prm[k][1], xk);
+    } else {
+      lp += (xk >= ep.prior_prm[k][2] && xk <= ep.prior_prm[k][3])
+                ? normlogpdf(ep.prior_prm[k][0], ep.prior_prm[k][1], xk) + ep.prior_const[k]
+                : -INFINITY;
+    }
+  }
+  return lp;
+}
+
+// counters[0] = #variances clamped to 0, counters[1] = min chunk-global index with variance < -1e-8 (init ~0ull)
+__global__ void __launch_bounds__(256)
+epilogue_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__ xq, const double* __restrict__ logprior,
+                const double* __restrict__ mean_at_xq, long long m_valid, long long mc, int nsplit, int T,
+                const double* __restrict__ mu_part, int have_var, const double* __restrict__ q_part,
+                double* __restrict__ mu_out, double* __restrict__ var_out, double* __restrict__ lp_out,
+                double* __restrict__ log_approx, double* __restrict__ log_mean, double* __restrict__ log_var,
+                unsigned long long* __restrict__ counters, unsigned long long index_base) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= m_valid) return;
+  const int p = ep.p;
+
+  double lp = 0.0;
+  if (ep.has_prior == 2) lp = logprior[m];
+  else if (ep.has_prior == 1) lp = log_prior_point(ep, xq + m * ep.d);
+
+  double plug = 0.0, lm = 0.0, lsq = 0.0;
+  for (int j = 0; j < p; ++j) {
+    double mu = 0.0;
+    for (int s = 0; s < nsplit; ++s) mu += mu_part[((size_t)s * p + j) * mc + m];
+    if (mean_at_xq) mu += mean_at_xq[m * p + j];
+    if (mu_out) mu_out[m * p + j] = mu;
+    const double z = ep.z[j], so = ep.so[j];
+    if (log_approx) plug += normlogpdf(mu, so, z);
+    if (have_var) {
+      double q = 0.0;
+      for (int t = 0; t < T; ++t) q += q_part[((size_t)t * p + j) * mc + m];
+      double var = ep.kxx[j] - q;
+      if (ep.pred_noise) var += ep.sig2[j];
+      if (ep.clamp_var && var < 0.0) var = 0.0;
+      if (var_out) var_out[m * p + j] = var;
+      const double so2 = so * so;
+      lm += normlogpdf(mu, sqrt(so2 + var), z);
+      lsq += normlogpdf(mu, sqrt((so2 + 2.0 * var) / 2.0), z);
+    }
+  }
+  if (lp_out) lp_out[m] = lp;
+  if (log_approx) log_approx[m] = lp + plug;
+  if (have_var) {
+    if (log_mean) log_mean[m] = lp + lm;
+    if (log_var) {
+      const double log_sq = ep.log_C + lsq;
+      double v = exp(log_sq) - exp(2.0 * lm);
+      if (v < 0.0) {
+        if (v >= -MAX_NEG_VAR) {
+          v = 0.0;
+          atomicAdd(&counters[0], 1ull);
+        } else {
+          atomicMin(&counters[1], index_base + (unsigned long long)m);
+        }
+      }
+      log_var[m] = 2.0 * lp + log(v);
+    }
+  }
+}
+
+int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* xq, const double* logprior,
+                    const double* mean_at_xq, int64_t m_valid, int64_t mc, int nsplit, const double* mu_part,
+                    bool have_var, const double* q_part, double* mu_out, double* var_out, double* lp_out,
+                    double* log_approx, double* log_mean, double* log_var, unsigned long long* counters,
+                    uint64_t index_base, cudaStream_t st) {
+  if (m_valid <= 0) return 0;
+  const int block = 256;
+  const unsigned grid = (unsigned)((m_valid + block - 1) / block);
+  epilogue_kernel<<<grid, block, 0, st>>>(ep, xq, logprior, mean_at_xq, (long long)m_valid, (long long)mc, nsplit, gp->T,
+                                          mu_part, have_var ? 1 : 0, q_part, mu_out, var_out, lp_out, log_approx,
+                                          log_mean, log_var, counters, (unsigned long long)index_base);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ argmax
+// Julia `argmax` semantics of BOSS's candidate maximisers: first maximal index; NaN never wins here.
+struct Best { double v; long long i; };
+__device__ __forceinline__ Best better(Best a, Best b) {
+  if (b.i < 0) return a;
+  if (a.i < 0) return b;
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ Best warp_best(Best x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best y; y.v = __shfl_xor_sync(0xffffffffu, x.v, o); y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = better(x, y);
+  }
+  return x;
+}
+__device__ __forceinline__ Best block_best(Best x) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  x = warp_best(x);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) { sv[w] = x.v; si[w] = x.i; }
+  __syncthreads();
+  if (w == 0) {
+    Best y; y.v = l < nw ? sv[l] : 0.0; y.i = l < nw ? si[l] : -1;
+    x = warp_best(y);
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+argmax_stage1(const double* __restrict__ vals, long long m_valid, long long offset, int exp_vals,
+              double* __restrict__ sv, long long* __restrict__ si) {
+  Best b; b.v = 0.0; b.i = -1;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < m_valid; m += (long long)gridDim.x * blockDim.x) {
+    double v = vals[m];
+    if (exp_vals) v = exp(v);
+    if (v == v && v > -INFINITY) { Best c; c.v = v; c.i = offset + m; b = better(b, c); }
+  }
+  b = block_best(b);
+  if (threadIdx.x == 0) { sv[blockIdx.x] = b.v; si[blockIdx.x] = b.i; }
+}
+__global__ void __launch_bounds__(256)
+argmax_stage2(const double* __restrict__ sv, const long long* __restrict__ si, int nblocks, double* best_val, long long* best_idx) {
+  Best b; b.v = 0.0; b.i = -1;
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { Best c; c.v = sv[k]; c.i = si[k]; b = better(b, c); }
+  b = block_best(b);
+  if (threadIdx.x == 0) {
+    Best cur; cur.v = *best_val; cur.i = *best_idx;
+    cur = better(cur, b);
+    *best_val = cur.v; *best_idx = cur.i;
+  }
+}
+
+int launch_argmax_chunk(Ctx* ctx, const double* vals, int64_t m_valid, int64_t global_offset, int exp_vals,
+                        double* scratch_val, long long* scratch_idx, double* best_val, long long* best_idx,
+                        cudaStream_t st) {
+  if (m_valid <= 0) return 0;
+  const int nblocks = (int)((m_valid + 2047) / 2048 < 1024 ? (m_valid + 2047) / 2048 : 1024);
+  argmax_stage1<<<nblocks, 256, 0, st>>>(vals, (long long)m_valid, (long long)global_offset, exp_vals, scratch_val, scratch_idx);
+  argmax_stage2<<<1, 256, 0, st>>>(scratch_val, scratch_idx, nblocks, best_val, best_idx);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ evidence sum
+// sum_i exp(log_post_i) / exp(log_prior_i)   (src/posterior/evidence.jl:20,22), fixed-order two-stage reduction
+__global__ void __launch_bounds__(256)
+ratio_sum_stage1(const double* __restrict__ log_post, const double* __restrict__ log_prior, long long m_valid,
+                 double* __restrict__ partial) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < m_valid; m += (long long)gridDim.x * blockDim.x)
+    s += exp(log_post[m]) / exp(log_prior[m]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void ratio_sum_stage2(const double* __restrict__ partial, int nblocks, double* accum) {
+  double s = 0.0;
+  for (int k = 0; k < nblocks; ++k) s += partial[k];
+  *accum += s;
+}
+
+int launch_sum_chunk(Ctx* ctx, const double* log_post, const double* log_prior, int64_t m_valid, double* scratch,
+                     double* accum, cudaStream_t st) {
+  if (m_valid <= 0) return 0;
+  const int nblocks = (int)((m_valid + 2047) / 2048 < 256 ? (m_valid + 2047) / 2048 : 256);
+  ratio_sum_stage1<<<nblocks, 256, 0, st>>>(log_post, log_prior, (long long)m_valid, scratch);
+  ratio_sum_stage2<<<1, 1, 0, st>>>(scratch, nblocks, accum);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ candidates
+struct CandParams {
+  int kind, d;
+  unsigned long long seed;
+  long long n_per_dim;
+  double lb[MAX_D], ub[MAX_D];
+};
+
+__global__ void __launch_bounds__(256)
+candidates_kernel(const __grid_constant__ CandParams cp, long long m, long long offset, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long gi = (unsigned long long)(offset + i);
+  if (cp.kind == BOSIP_B200_CAND_PHILOX) {
+    for (int k = 0; k < cp.d; ++k) {
+      const double u = philox_unit(cp.seed, gi, k);
+      out[i * cp.d + k] = __dadd_rn(cp.lb[k], __dmul_rn(__dsub_rn(cp.ub[k], cp.lb[k]), u));
+    }
+  } else {  // tensor grid, first coordinate fastest; matches numpy.linspace(lb, ub, n) per axis
+    unsigned long long r = gi;
+    const unsigned long long n = (unsigned long long)cp.n_per_dim;
+    for (int k = 0; k < cp.d; ++k) {
+      const unsigned long long ik = r % n;
+      r /= n;
+      double x;
+      if (n == 1) x = cp.lb[k];
+      else if (ik == n - 1) x = cp.ub[k];
+      else x = __dadd_rn(__dmul_rn((double)ik, __ddiv_rn(__dsub_rn(cp.ub[k], cp.lb[k]), (double)(n - 1))), cp.lb[k]);
+      out[i * cp.d + k] = x;
+    }
+  }
+}
+
+int launch_candidates(Ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t m, int64_t offset, double* out,
+                      cudaStream_t st) {
+  if (m <= 0) return 0;
+  if (d > MAX_D) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "d exceeds MAX_D");
+  if (!src->lb || !src->ub) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "candidate source needs lb and ub");
+  CandParams cp;
+  cp.kind = src->kind; cp.d = d; cp.seed = src->seed; cp.n_per_dim = src->n_per_dim;
+  for (int k = 0; k < d; ++k) { cp.lb[k] = src->lb[k]; cp.ub[k] = src->ub[k]; }
+  candidates_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(cp, (long long)m, (long long)offset, out);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bosip

@@ -1,0 +1,128 @@
+// Cross-kernel K(X*, X) + predictive mean  (replaces BOSS.mean(model_post, X): K* formation and the GEMV
+// mu = K* a, call sites /root/reference/src/posterior/likelihood.jl:8,12,21,25 and src/likelihoods/normal.jl:37-68).
+//
+// One CTA = 128 query points (one per thread) x one n-span of training points x one output j.
+// The scaled training inputs U_j (SoA, d rows) and the weights alpha_j^2 a_j of the span are staged into shared
+// memory by 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) signalled on an mbarrier; every thread then walks the span
+// four training points at a time (broadcast LDS.128), evaluates the ARD SE / Matern kernel in FP64, accumulates the
+// mean privately (no shuffles needed: a thread owns its query row) and, when the variance is wanted, writes the four
+// K* values as one 32-byte group into the k-chunk-major, XOR-swizzled workspace the variance GEMM bulk-loads.
+#include "common.cuh"
+
+namespace bosip {
+
+template <int KERNEL>
+__device__ __forceinline__ double kernel_value(double r2) {
+  // r2 already carries the kernel constant (scale = c/lambda with c = 1/sqrt2, sqrt3, sqrt5), SURVEY.md App. A.1
+  if (KERNEL == BOSIP_B200_KERNEL_SE) return exp(-r2);
+  double s = sqrt(r2);
+  if (KERNEL == BOSIP_B200_KERNEL_MATERN32) return (1.0 + s) * exp(-s);
+  return (1.0 + s + r2 * (1.0 / 3.0)) * exp(-s);
+}
+
+template <int KERNEL, int DP, bool WRITE_K>
+__global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict__ Us, const double* __restrict__ scale,
+                                                       const double* __restrict__ As, int Ns, int d,
+                                                       const double* __restrict__ xq, long long m_valid, long long mc,
+                                                       int nspan, double* __restrict__ Ks, double* __restrict__ mu_part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* su = reinterpret_cast<double*>(smem_raw);          // [DP][nspan]
+  double* sa = su + (size_t)DP * nspan;                       // [nspan]
+  __shared__ __align__(8) uint64_t bar;
+
+  const int j = blockIdx.z, split = blockIdx.y, p = gridDim.z;
+  const int n0 = split * nspan;
+  const int len = min(nspan, Ns - n0);  // multiple of 16
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    const uint32_t row_bytes = (uint32_t)len * 8u;
+    mbar_expect_tx(&bar, row_bytes * (DP + 1));
+#pragma unroll 1
+    for (int k = 0; k < DP; ++k) bulk_g2s(su + (size_t)k * nspan, Us + ((size_t)j * DP + k) * Ns + n0, row_bytes, &bar);
+    bulk_g2s(sa, As + (size_t)j * Ns + n0, row_bytes, &bar);
+  }
+
+  const long long m = (long long)blockIdx.x * TILE_M + tid;
+  const long long m_src = m < m_valid ? m : m_valid - 1;
+  double uq[DP];
+#pragma unroll
+  for (int k = 0; k < DP; ++k) uq[k] = (k < d) ? xq[m_src * d + k] * scale[j * DP + k] : 0.0;
+
+  __syncthreads();  // barrier init visible to all waiters
+  mbar_wait(&bar, 0);
+
+  double acc = 0.0;
+  const int row_sw = (int)(m & 3);
+#pragma unroll 1
+  for (int n = 0; n < len; n += 4) {
+    double r2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      const double2 u01 = *reinterpret_cast<const double2*>(su + (size_t)k * nspan + n);
+      const double2 u23 = *reinterpret_cast<const double2*>(su + (size_t)k * nspan + n + 2);
+      double t0 = uq[k] - u01.x, t1 = uq[k] - u01.y, t2 = uq[k] - u23.x, t3 = uq[k] - u23.y;
+      r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]); r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
+    }
+    double kv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) kv[e] = kernel_value<KERNEL>(r2[e]);
+    const double2 a01 = *reinterpret_cast<const double2*>(sa + n);
+    const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 2);
+    acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);
+    if (WRITE_K) {
+      const int ng = n0 + n;            // global training index of the group (multiple of 4)
+      const int kc = ng >> 4;           // k-chunk
+      const int grp = ((ng >> 2) ^ row_sw) & 3;
+      double* dst = Ks + (((size_t)j * (Ns >> 4) + kc) * mc + m) * TILE_K + grp * 4;
+      *reinterpret_cast<double2*>(dst) = make_double2(kv[0], kv[1]);
+      *reinterpret_cast<double2*>(dst + 2) = make_double2(kv[2], kv[3]);
+    }
+  }
+  mu_part[((size_t)split * p + j) * mc + m] = acc;
+}
+
+template <int KERNEL, int DP>
+static int launch_kd(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
+                     double* Ks, double* mu_part, bool write_k, cudaStream_t st) {
+  dim3 grid((unsigned)m_tiles, (unsigned)nsplit, (unsigned)gp->p);
+  size_t smem = (size_t)(DP + 1) * nspan * sizeof(double);
+  if (write_k) {
+    auto kern = kstar_kernel<KERNEL, DP, true>;
+    BOSIP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TILE_M, smem, st>>>(gp->Us, gp->scale, gp->As, gp->Ns, gp->d, xq, m_valid, mc, nspan, Ks, mu_part);
+  } else {
+    auto kern = kstar_kernel<KERNEL, DP, false>;
+    BOSIP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TILE_M, smem, st>>>(gp->Us, gp->scale, gp->As, gp->Ns, gp->d, xq, m_valid, mc, nspan, Ks, mu_part);
+  }
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+template <int KERNEL>
+static int launch_k(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
+                    double* Ks, double* mu_part, bool write_k, cudaStream_t st) {
+#define BOSIP_DP_CASE(DPV) \
+  case DPV: return launch_kd<KERNEL, DPV>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
+  switch (gp->dp) {
+    BOSIP_DP_CASE(2) BOSIP_DP_CASE(3) BOSIP_DP_CASE(4) BOSIP_DP_CASE(5) BOSIP_DP_CASE(6) BOSIP_DP_CASE(8)
+    BOSIP_DP_CASE(10) BOSIP_DP_CASE(12) BOSIP_DP_CASE(16) BOSIP_DP_CASE(24) BOSIP_DP_CASE(32)
+  }
+#undef BOSIP_DP_CASE
+  BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unsupported padded dimension");
+}
+
+int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
+                 double* Ks, double* mu_part, bool write_k, cudaStream_t st) {
+  switch (gp->kernel_id) {
+    case BOSIP_B200_KERNEL_SE: return launch_k<BOSIP_B200_KERNEL_SE>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
+    case BOSIP_B200_KERNEL_MATERN32: return launch_k<BOSIP_B200_KERNEL_MATERN32>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
+    case BOSIP_B200_KERNEL_MATERN52: return launch_k<BOSIP_B200_KERNEL_MATERN52>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
+  }
+  BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown kernel id");
+}
+
+}  // namespace bosip

@@ -1,0 +1,299 @@
+// Metrics of /root/reference/src/metrics: the MMD pairwise-kernel sums (mmd.jl:23-28) and the TV distance on a weighted
+// grid (tv.jl:59-73 with logsumexp/logmeanexp of src/utils/utils.jl:7-15).
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bosip {
+
+// ================================================================================================ MMD
+// sum_{i,j} k(P_i, Q_j) for a 128-row tile x a strip of column tiles.  Thread = row point (coordinates in registers),
+// column tile staged in shared memory (SoA) and read as broadcasts.  In symmetric mode (P == Q) only column tiles
+// >= row tile are visited, off-diagonal tiles weighted 2: the result is still the full V-statistic incl. diagonal.
+constexpr int MMD_TILE = 128;
+constexpr int MMD_STRIP = 16;  // column tiles per CTA
+
+template <int KERNEL>
+__device__ __forceinline__ double mmd_kval(double r2) {
+  if (KERNEL == BOSIP_B200_KERNEL_SE) return exp(-r2);
+  double s = sqrt(r2);
+  if (KERNEL == BOSIP_B200_KERNEL_MATERN32) return (1.0 + s) * exp(-s);
+  return (1.0 + s + r2 * (1.0 / 3.0)) * exp(-s);
+}
+
+// Ps/Qs: scaled points, SoA [dp][np] / [dp][nq] (zero padded to multiples of 128 in count; padded points are masked)
+template <int KERNEL, int DP>
+__global__ void __launch_bounds__(MMD_TILE)
+mmd_kernel(const double* __restrict__ Ps, long long np, long long np_pad, const double* __restrict__ Qs, long long nq,
+           long long nq_pad, int symmetric, int rank, int world, double* __restrict__ partial) {
+  __shared__ __align__(16) double sq[DP][MMD_TILE];
+  __shared__ double red[MMD_TILE];
+  const long long cta = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+  const int rt = blockIdx.x;                    // row tile
+  const int ct0 = blockIdx.y * MMD_STRIP;       // first column tile of the strip
+  const int n_ct = (int)(nq_pad / MMD_TILE);
+  double total = 0.0;
+  const bool mine = (cta % world) == rank;
+  if (mine && !(symmetric && ct0 + MMD_STRIP - 1 < rt)) {
+    const long long i = (long long)rt * MMD_TILE + threadIdx.x;
+    double pi[DP];
+#pragma unroll
+    for (int k = 0; k < DP; ++k) pi[k] = Ps[(size_t)k * np_pad + i];
+    const bool row_ok = i < np;
+    for (int ct = ct0; ct < min(ct0 + MMD_STRIP, n_ct); ++ct) {
+      if (symmetric && ct < rt) continue;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < DP; ++k) sq[k][threadIdx.x] = Qs[(size_t)k * nq_pad + (size_t)ct * MMD_TILE + threadIdx.x];
+      __syncthreads();
+      const int jmax = (int)min((long long)MMD_TILE, nq - (long long)ct * MMD_TILE);
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      int jj = 0;
+      for (; jj + 4 <= jmax; jj += 4) {
+        double r2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          const double2 q01 = *reinterpret_cast<const double2*>(&sq[k][jj]);
+          const double2 q23 = *reinterpret_cast<const double2*>(&sq[k][jj + 2]);
+          double t0 = pi[k] - q01.x, t1 = pi[k] - q01.y, t2 = pi[k] - q23.x, t3 = pi[k] - q23.y;
+          r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]); r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += mmd_kval<KERNEL>(r2[e]);
+      }
+      for (; jj < jmax; ++jj) {
+        double r2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) { const double t = pi[k] - sq[k][jj]; r2 = fma(t, t, r2); }
+        acc[0] += mmd_kval<KERNEL>(r2);
+      }
+      const double w = (symmetric && ct != rt) ? 2.0 : 1.0;
+      if (row_ok) total += w * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    }
+  }
+  red[threadIdx.x] = total;
+  __syncthreads();
+  for (int o = MMD_TILE / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[cta] = red[0];
+}
+
+// fixed-order tree sum of `n` partials into out[0] (one block)
+__global__ void __launch_bounds__(1024) tree_sum_kernel(const double* __restrict__ partial, long long n, double* out) {
+  __shared__ double red[1024];
+  double s = 0.0;
+  for (long long k = threadIdx.x; k < n; k += 1024) s += partial[k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// AoS d x n (column-major) -> scaled SoA [dp][n_pad]
+__global__ void mmd_scale_kernel(const double* __restrict__ P, long long n, long long n_pad, int d, int dp,
+                                 const double* __restrict__ scale, double* __restrict__ Ps) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (i >= n_pad) return;
+  Ps[(size_t)k * n_pad + i] = (i < n && k < d) ? P[(size_t)k + (size_t)d * i] * scale[k] : 0.0;
+}
+
+template <int KERNEL, int DP>
+static void mmd_launch(const double* Ps, long long np, long long npp, const double* Qs, long long nq, long long nqp, int sym,
+                       int rank, int world, double* partial, dim3 grid, cudaStream_t st) {
+  mmd_kernel<KERNEL, DP><<<grid, MMD_TILE, 0, st>>>(Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial);
+}
+
+template <int KERNEL>
+static int mmd_launch_k(Ctx* ctx, int dp, const double* Ps, long long np, long long npp, const double* Qs, long long nq,
+                        long long nqp, int sym, int rank, int world, double* partial, dim3 grid, cudaStream_t st) {
+#define BOSIP_DP_CASE(DPV) \
+  case DPV: mmd_launch<KERNEL, DPV>(Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st); break;
+  switch (dp) {
+    BOSIP_DP_CASE(2) BOSIP_DP_CASE(3) BOSIP_DP_CASE(4) BOSIP_DP_CASE(5) BOSIP_DP_CASE(6) BOSIP_DP_CASE(8)
+    BOSIP_DP_CASE(10) BOSIP_DP_CASE(12) BOSIP_DP_CASE(16) BOSIP_DP_CASE(24) BOSIP_DP_CASE(32)
+    default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unsupported dimension");
+  }
+#undef BOSIP_DP_CASE
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+static int mmd_pair(Ctx* ctx, int kernel_id, int dp, const double* Ps, long long np, long long npp, const double* Qs,
+                    long long nq, long long nqp, int sym, int rank, int world, double* partial, double* out,
+                    cudaStream_t st) {
+  dim3 grid((unsigned)(npp / MMD_TILE), (unsigned)((nqp / MMD_TILE + MMD_STRIP - 1) / MMD_STRIP));
+  const long long nparts = (long long)grid.x * grid.y;
+  switch (kernel_id) {
+    case 0: BOSIP_TRY((mmd_launch_k<0>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st))); break;
+    case 1: BOSIP_TRY((mmd_launch_k<1>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st))); break;
+    case 2: BOSIP_TRY((mmd_launch_k<2>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st))); break;
+    default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown kernel id");
+  }
+  tree_sum_kernel<<<1, 1024, 0, st>>>(partial, nparts, out);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double* A, int64_t n, const double* B,
+             int64_t m, int mem, int rank, int world, double* sums) {
+  if (d < 1 || d > MAX_D || n < 1 || m < 1 || !A || !B || !lambda || !sums) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad MMD arguments");
+  if (world < 1 || rank < 0 || rank >= world) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad rank/world");
+  const int dp = pad_dim(d);
+  const long long np = round_up(n, MMD_TILE), mp = round_up(m, MMD_TILE);
+  cudaStream_t st = ctx->s_comp;
+  const double ck = kernel_id == BOSIP_B200_KERNEL_SE ? sqrt(0.5) : kernel_id == BOSIP_B200_KERNEL_MATERN32 ? sqrt(3.0) : sqrt(5.0);
+  std::vector<double> h_scale(dp, 0.0);
+  for (int k = 0; k < d; ++k) {
+    if (!(lambda[k] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "length-scales must be > 0");
+    h_scale[k] = ck / lambda[k];
+  }
+  double *dA = nullptr, *dB = nullptr, *As = nullptr, *Bs = nullptr, *dscale = nullptr, *partial = nullptr, *dout = nullptr;
+  struct Tmps { double** v[7]; ~Tmps() { for (auto q : v) if (*q) cudaFree(*q); } } tmps{{&dA, &dB, &As, &Bs, &dscale, &partial, &dout}};
+  const long long max_tiles = (np > mp ? np : mp) / MMD_TILE;
+  const long long max_parts = max_tiles * ((max_tiles + MMD_STRIP - 1) / MMD_STRIP);
+  BOSIP_CUDA(ctx, cudaMalloc(&As, (size_t)dp * np * 8));
+  BOSIP_CUDA(ctx, cudaMalloc(&Bs, (size_t)dp * mp * 8));
+  BOSIP_CUDA(ctx, cudaMalloc(&dscale, dp * 8));
+  BOSIP_CUDA(ctx, cudaMalloc(&partial, (size_t)max_parts * 8));
+  BOSIP_CUDA(ctx, cudaMalloc(&dout, 3 * 8));
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(dscale, h_scale.data(), dp * 8, cudaMemcpyHostToDevice, st));
+  const double *pA = A, *pB = B;
+  if (mem == BOSIP_B200_HOST) {
+    BOSIP_CUDA(ctx, cudaMalloc(&dA, (size_t)d * n * 8));
+    BOSIP_CUDA(ctx, cudaMalloc(&dB, (size_t)d * m * 8));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(dA, A, (size_t)d * n * 8, cudaMemcpyHostToDevice, st));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(dB, B, (size_t)d * m * 8, cudaMemcpyHostToDevice, st));
+    pA = dA; pB = dB;
+  }
+  mmd_scale_kernel<<<dim3((unsigned)((np + 255) / 256), dp), 256, 0, st>>>(pA, n, np, d, dp, dscale, As);
+  mmd_scale_kernel<<<dim3((unsigned)((mp + 255) / 256), dp), 256, 0, st>>>(pB, m, mp, d, dp, dscale, Bs);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, As, n, np, As, n, np, 1, rank, world, partial, dout + 0, st));
+  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, Bs, m, mp, Bs, m, mp, 1, rank, world, partial, dout + 1, st));
+  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, As, n, np, Bs, m, mp, 0, rank, world, partial, dout + 2, st));
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(sums, dout, 3 * 8, cudaMemcpyDeviceToHost, st));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ================================================================================================ TV
+// Online log-sum-exp pair (max, sum exp(. - max)); -Inf-safe merge in a fixed order.
+struct Lse { double m, s; };
+__host__ __device__ inline Lse lse_merge(Lse a, Lse b) {
+  if (b.m == -INFINITY) return a;
+  if (a.m == -INFINITY) return b;
+  Lse r;
+  if (a.m >= b.m) { r.m = a.m; r.s = (a.m == INFINITY) ? a.s : a.s + b.s * exp(b.m - a.m); }
+  else { r.m = b.m; r.s = (b.m == INFINITY) ? b.s : b.s + a.s * exp(a.m - b.m); }
+  return r;
+}
+__device__ __forceinline__ void lse_push(Lse& a, double v) {
+  if (v == -INFINITY) return;
+  if (v > a.m) { a.s = (a.m == -INFINITY) ? 1.0 : a.s * exp(a.m - v) + 1.0; a.m = v; }
+  else a.s += (v == INFINITY) ? 1.0 : exp(v - a.m);
+}
+__device__ __forceinline__ Lse lse_block(Lse x, Lse* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Lse y; y.m = __shfl_down_sync(0xffffffffu, x.m, o); y.s = __shfl_down_sync(0xffffffffu, x.s, o);
+    x = lse_merge(x, y);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    Lse y; y.m = -INFINITY; y.s = 0.0;
+    if (l < (int)(blockDim.x >> 5)) y = sh[l];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Lse z; z.m = __shfl_down_sync(0xffffffffu, y.m, o); z.s = __shfl_down_sync(0xffffffffu, y.s, o);
+      y = lse_merge(y, z);
+    }
+    x = y;
+  }
+  return x;
+}
+
+// out[block] = {max_a, sum_a, max_t, sum_t}
+__global__ void __launch_bounds__(256)
+tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
+                 double* __restrict__ out) {
+  __shared__ Lse sh[8];
+  Lse la{-INFINITY, 0.0}, lt{-INFINITY, 0.0};
+  // contiguous slice per block keeps the merge order independent of the launch geometry's interleaving
+  const long long per = (G + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double w = lw[i];
+    lse_push(la, w + a[i]);
+    lse_push(lt, w + t[i]);
+  }
+  la = lse_block(la, sh);
+  lt = lse_block(lt, sh);
+  if (threadIdx.x == 0) { out[4 * blockIdx.x + 0] = la.m; out[4 * blockIdx.x + 1] = la.s; out[4 * blockIdx.x + 2] = lt.m; out[4 * blockIdx.x + 3] = lt.s; }
+}
+
+// out[block] = {max, sum} of lw + log|exp(a - eva) - exp(t - evt)|   (tv.jl:64-70)
+__global__ void __launch_bounds__(256)
+tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
+                 double eva, double evt, int a_inf, int t_inf, double* __restrict__ out) {
+  __shared__ Lse sh[8];
+  Lse ld{-INFINITY, 0.0};
+  const long long per = (G + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double ea = a_inf ? 0.0 : exp(a[i] - eva);
+    const double et = t_inf ? 0.0 : exp(t[i] - evt);
+    lse_push(ld, lw[i] + log(fabs(ea - et)));
+  }
+  ld = lse_block(ld, sh);
+  if (threadIdx.x == 0) { out[2 * blockIdx.x + 0] = ld.m; out[2 * blockIdx.x + 1] = ld.s; }
+}
+
+static int tv_common(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, int stage, double eva,
+                     double evt, double* out) {
+  if (G < 1 || !lw || !a || !t || !out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad TV arguments");
+  cudaStream_t st = ctx->s_comp;
+  double *dl = nullptr, *da = nullptr, *dt = nullptr, *dpart = nullptr;
+  struct Tmps { double** v[4]; ~Tmps() { for (auto q : v) if (*q) cudaFree(*q); } } tmps{{&dl, &da, &dt, &dpart}};
+  const double *pl = lw, *pa = a, *pt = t;
+  if (mem == BOSIP_B200_HOST) {
+    BOSIP_CUDA(ctx, cudaMalloc(&dl, (size_t)G * 8)); BOSIP_CUDA(ctx, cudaMalloc(&da, (size_t)G * 8)); BOSIP_CUDA(ctx, cudaMalloc(&dt, (size_t)G * 8));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(dl, lw, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(da, a, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(dt, t, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    pl = dl; pa = da; pt = dt;
+  }
+  const int nblocks = (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 8 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 8);
+  const int width = stage == 1 ? 4 : 2;
+  BOSIP_CUDA(ctx, cudaMalloc(&dpart, (size_t)nblocks * width * 8));
+  if (stage == 1) tv_stage1_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, dpart);
+  else tv_stage2_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, eva, evt, isinf(eva) ? 1 : 0, isinf(evt) ? 1 : 0, dpart);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  std::vector<double> h((size_t)nblocks * width);
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(h.data(), dpart, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int c = 0; c < width / 2; ++c) {
+    Lse acc{-INFINITY, 0.0};
+    for (int b = 0; b < nblocks; ++b) acc = lse_merge(acc, Lse{h[(size_t)b * width + 2 * c], h[(size_t)b * width + 2 * c + 1]});
+    out[2 * c] = acc.m; out[2 * c + 1] = acc.s;
+  }
+  return 0;
+}
+
+int tv_stage1(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* out4) {
+  return tv_common(ctx, lw, a, t, G, mem, 1, 0.0, 0.0, out4);
+}
+int tv_stage2(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double eva, double evt, double* out2) {
+  return tv_common(ctx, lw, a, t, G, mem, 2, eva, evt, out2);
+}
+
+}  // namespace bosip

@@ -1,0 +1,200 @@
+/* bosip_b200.h -- C ABI of libbosip_b200.so: the B200 (sm_100a) evaluator for BOSIP.jl's batched
+ * GP-posterior / likelihood / acquisition / metric path.
+ *
+ * Every entry point is what the reference's host language (Julia, `ccall`) would bind for this path; the
+ * reference interface each one replaces is cited as file:line relative to the BOSIP.jl v0.5.2 tree.
+ * INTEGRATION.md shows the Julia-side `ccall` stubs.
+ *
+ * Conventions
+ *   - All matrices are COLUMN-MAJOR Float64 exactly as Julia stores them: a d x M `Matrix{Float64}` is M
+ *     contiguous d-tuples.  GP outputs are p x M (reference: test/unit/utils.jl:8-11).
+ *   - Every function returns 0 (BOSIP_B200_OK) or a negative error code; the message is available from
+ *     bosip_b200_last_error().  Nothing aborts the process.
+ *   - Buffers are owned by the caller.  `mem` says where the *large* query/output buffers live:
+ *     BOSIP_B200_HOST (plain or pinned host memory; the library stages H2D/D2H, overlapped with compute) or
+ *     BOSIP_B200_DEVICE (device pointers on the context's GPU; used when inputs are already resident in HBM).
+ *     Small parameter arrays (hyper-parameters, z_obs, priors ...) are always host pointers.
+ *   - Calls are synchronous (they return when outputs are complete) and thread-safe per context.
+ *   - There is NO CPU fallback: without a CUDA device bosip_b200_init() fails with BOSIP_B200_ECUDA.
+ */
+#ifndef BOSIP_B200_H
+#define BOSIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOSIP_B200_VERSION 100
+
+/* error codes */
+#define BOSIP_B200_OK 0
+#define BOSIP_B200_EINVAL (-1)   /* bad argument                                                         */
+#define BOSIP_B200_ECUDA (-2)    /* CUDA runtime failure (message holds cudaGetErrorString)                  */
+#define BOSIP_B200_ENOTPD (-3)   /* Cholesky met a non-positive pivot   (Julia: PosDefException)             */
+#define BOSIP_B200_EDOMAIN (-4)  /* likelihood variance < -1e-8          (Julia: DomainError, src/posterior/likelihood.jl:61-65) */
+#define BOSIP_B200_ENOMEM (-5)   /* device/host allocation failure                                           */
+
+/* kernels: KernelFunctions.SqExponentialKernel / Matern32Kernel / Matern52Kernel under
+ * with_lengthscale(k, lambda_j)  (examples/simple/main.jl:36, examples/interactive/toy_problem.jl:58) */
+#define BOSIP_B200_KERNEL_SE 0
+#define BOSIP_B200_KERNEL_MATERN32 1
+#define BOSIP_B200_KERNEL_MATERN52 2
+
+/* memory space of the large buffers */
+#define BOSIP_B200_HOST 0
+#define BOSIP_B200_DEVICE 1
+
+/* `want` bitmask of bosip_b200_posterior_eval */
+#define BOSIP_B200_WANT_APPROX 1u /* log_approx_posterior   src/posterior/log_posterior.jl:15-21 */
+#define BOSIP_B200_WANT_MEAN 2u   /* log_posterior_mean     src/posterior/log_posterior.jl:35-41 */
+#define BOSIP_B200_WANT_VAR 4u    /* log_posterior_variance src/posterior/log_posterior.jl:55-61 */
+
+/* acquisitions: src/acquisitions/maxvar.jl:9-11, src/acquisitions/logmaxvar.jl:13-15 */
+#define BOSIP_B200_ACQ_MAXVAR 0
+#define BOSIP_B200_ACQ_LOGMAXVAR 1
+
+/* univariate prior kinds of a product prior (src/types/problem.jl:33 `x_prior`; the examples use
+ * Product of Uniform / Normal / truncated(Normal): examples/interactive/toy_problem.jl:43,
+ * docs/src/example.md:52-55, examples/simple/toy_problem.jl:31) */
+#define BOSIP_B200_PRIOR_UNIFORM 0     /* params: a, b          */
+#define BOSIP_B200_PRIOR_NORMAL 1      /* params: m, s          */
+#define BOSIP_B200_PRIOR_TRUNCNORMAL 2 /* params: m, s, a, b    */
+
+/* candidate sources of bosip_b200_acq_argmax */
+#define BOSIP_B200_CAND_POINTS 0 /* explicit d x M matrix (host or device)                                  */
+#define BOSIP_B200_CAND_PHILOX 1 /* U(lb,ub)^d generated on device, Philox4x32-10 keyed by the global index */
+#define BOSIP_B200_CAND_GRID 2   /* tensor grid: n_per_dim points per dimension, first coordinate fastest   */
+
+typedef struct bosip_b200_ctx bosip_b200_ctx; /* one per (process, GPU) */
+typedef struct bosip_b200_gp bosip_b200_gp;   /* a conditioned GP = BOSS.ModelPosterior handle */
+
+/* Options whose BOSS-side semantics could not be verified: parameters, not constants. */
+typedef struct {
+  double jitter;     /* extra diagonal variance added to K (AbstractGPs FiniteGP default 1e-18); default 0      */
+  int32_t pred_noise; /* 1: predictive variance includes sigma_j^2; default 0 (latent f)                          */
+  int32_t clamp_var;  /* 1: negative predictive variances are clamped to 0 before sqrt; default 1                 */
+} bosip_b200_gp_opts;
+
+/* NormalLikelihood(z_obs, std_obs): src/likelihoods/normal.jl:16-19 */
+typedef struct {
+  int32_t p;
+  const double* z_obs;   /* p */
+  const double* std_obs; /* p, > 0 */
+} bosip_b200_like_normal;
+
+/* Product prior descriptor, or host-supplied log-prior values. */
+typedef struct {
+  int32_t d;
+  const int32_t* kind;    /* d entries BOSIP_B200_PRIOR_*; NULL => no prior term (log prior = 0)             */
+  const double* params;   /* d x 4 row-major: per dimension (p0,p1,p2,p3) as listed above                   */
+  const double* logprior; /* optional: M precomputed log-prior values in the same memory space as Xq; when
+                             non-NULL it replaces the descriptor (any MultivariateDistribution on the Julia side) */
+} bosip_b200_prior;
+
+typedef struct {
+  int32_t kind;          /* BOSIP_B200_CAND_*                                                              */
+  int32_t mem;           /* POINTS: memory space of `points`                                               */
+  const double* points;  /* POINTS: d x M                                                                  */
+  uint64_t seed;         /* PHILOX                                                                         */
+  const double* lb;      /* PHILOX / GRID: d lower bounds                                                  */
+  const double* ub;      /* PHILOX / GRID: d upper bounds                                                  */
+  int64_t n_per_dim;     /* GRID                                                                           */
+} bosip_b200_cand_src;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+int bosip_b200_version(void);
+/* Create a context on CUDA device `device`.  Fails (ECUDA) when no such device exists: there is no CPU path. */
+int bosip_b200_init(int device, bosip_b200_ctx** out);
+int bosip_b200_shutdown(bosip_b200_ctx* ctx);
+/* Last error message of this context (ctx == NULL: of the last failed bosip_b200_init on this thread). */
+const char* bosip_b200_last_error(const bosip_b200_ctx* ctx);
+/* Upper bound for the number of query points processed per internal chunk (0 = library default). */
+int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
+
+/* ---- GP conditioning: replaces BOSS.model_posterior(bosip.problem)
+ *      (src/posterior/log_posterior.jl:81,115,148,182,214) --------------------------------------------- */
+/* X d x N, Y p x N, lambda d x p, alpha p, sigma p (src/subset_problem.jl:38-50); mean_at_X p x N or NULL.
+ * Builds K_j = alpha_j^2 k(X/lambda_j) + (sigma_j^2 + jitter) I, factorises it with the hand-written blocked
+ * FP64 Cholesky, forms L_j^{-1} and a_j = K_j^{-1}(Y_j - m_j(X)) on the device. */
+int bosip_b200_gp_fit(bosip_b200_ctx* ctx, int kernel_id, int d, int N, int p, const double* X, const double* Y,
+                      const double* lambda, const double* alpha, const double* sigma, const double* mean_at_X,
+                      const bosip_b200_gp_opts* opts, bosip_b200_gp** out);
+/* Same, but the factorisation comes from the host (exact-parity runs): L is p matrices N x N column-major
+ * (lower triangle read), a is N x p. */
+int bosip_b200_gp_load_factors(bosip_b200_ctx* ctx, int kernel_id, int d, int N, int p, const double* X,
+                               const double* lambda, const double* alpha, const double* sigma, const double* L,
+                               const double* a, const bosip_b200_gp_opts* opts, bosip_b200_gp** out);
+/* Download what the device holds (any pointer may be NULL): L (p x N x N col-major), Linv (same layout),
+ * a (N x p).  For tests and for ncclBroadcast-free host replication. */
+int bosip_b200_gp_get_factors(bosip_b200_gp* gp, double* L, double* Linv, double* a);
+int bosip_b200_gp_free(bosip_b200_gp* gp);
+
+/* ---- BOSS.mean / var / mean_and_var (model_post, X::AbstractMatrix)  -> p x M
+ *      (src/posterior/likelihood.jl:8,12,21,25; src/likelihoods/normal.jl:37,43,60,68) ------------------ */
+/* mean_at_Xq: p x M prior-mean values m_j(Xq) or NULL (zero mean).  var may be NULL (mean only). */
+int bosip_b200_gp_predict(bosip_b200_gp* gp, const double* Xq, int64_t M, int mem, const double* mean_at_Xq,
+                          double* mu, double* var);
+
+/* ---- fused posterior closures (src/posterior/log_posterior.jl:15-61 over src/posterior/likelihood.jl:19-59
+ *      and src/likelihoods/normal.jl:28-79): ONE GP predict per point, all requested outputs at once. ------ */
+/* Outputs (each M doubles or NULL, selected by `want`): log_approx_post, log_post_mean, log_post_var.
+ * n_clamped (optional) counts likelihood variances in [-1e-8, 0) clamped to 0 (=> -Inf).  A variance
+ * < -1e-8 returns BOSIP_B200_EDOMAIN like the reference's DomainError. */
+int bosip_b200_posterior_eval(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                              const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
+                              double* log_approx_post, double* log_post_mean, double* log_post_var,
+                              int64_t* n_clamped);
+
+/* ---- acquisition over a candidate set + argmax: MaxVar / LogMaxVar closure (src/acquisitions/maxvar.jl:9-11,
+ *      logmaxvar.jl:13-15) evaluated by BOSS's SamplingAM / GridAM (docs/src/hyperparams.md:69). ----------- */
+/* Candidates index_offset .. index_offset+M-1 of the source (so that ranks can shard one global set).
+ * Ties resolve to the lowest global index (Julia `argmax`); NaN values are never selected.
+ * best_idx is the GLOBAL 0-based index, best_x the d coordinates of the winner; if every value is -Inf/NaN
+ * best_idx = -1. */
+int bosip_b200_acq_argmax(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                          const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq,
+                          int64_t* best_idx, double* best_val, double* best_x);
+/* Materialise candidates index_offset.. of a PHILOX/GRID source into `out` (d x M, memory space `mem`). */
+int bosip_b200_candidates(bosip_b200_ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t M,
+                          int64_t index_offset, int mem, double* out);
+
+/* ---- evidence (src/posterior/evidence.jl:19-24): sum_i post(x_i)/pdf(prior, x_i) over the given prior
+ *      samples xs (d x S).  which = BOSIP_B200_WANT_APPROX or BOSIP_B200_WANT_MEAN selects the posterior.
+ *      Returns the SUM and the count so that ranks can all-reduce; evidence = sum / S. -------------------- */
+int bosip_b200_evidence_sum(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                            const double* xs, int64_t S, int mem, unsigned which, double* sum_out);
+
+/* ---- MMD (src/metrics/mmd.jl:23-28): biased V-statistic.  A d x n, B d x m, lambda d (ARD length-scales of
+ *      with_lengthscale).  sums_out[3] = {sum k(A,A), sum k(B,B), sum k(A,B)} over THIS rank's share of the
+ *      tile grid (rank/world = 0/1 for the whole problem); mmd2 = sAA/n^2 + sBB/m^2 - 2 sAB/(n m). ------- */
+int bosip_b200_mmd_sums(bosip_b200_ctx* ctx, int kernel_id, int d, const double* lambda, const double* A, int64_t n,
+                        const double* B, int64_t m, int mem, int rank, int world, double* sums_out);
+int bosip_b200_mmd(bosip_b200_ctx* ctx, int kernel_id, int d, const double* lambda, const double* A, int64_t n,
+                   const double* B, int64_t m, int mem, double* mmd2_out);
+
+/* ---- TV (src/metrics/tv.jl:59-73 with logsumexp/logmeanexp of src/utils/utils.jl:7-15) ------------------ */
+/* stage 1: out[4] = {max(lw+a), sum exp(lw+a-max), max(lw+t), sum exp(lw+t-max)} over this rank's G points.
+ * stage 2: given the global ev_approx/ev_true (logmeanexp), out[2] = {max, sum exp(.-max)} of
+ *          lw + log|exp(a-ev_a) - exp(t-ev_t)|.   bosip_b200_tv = both stages on one GPU. */
+int bosip_b200_tv_stage1(bosip_b200_ctx* ctx, const double* log_ws, const double* a, const double* t, int64_t G,
+                         int mem, double* out4);
+int bosip_b200_tv_stage2(bosip_b200_ctx* ctx, const double* log_ws, const double* a, const double* t, int64_t G,
+                         int mem, double ev_approx, double ev_true, double* out2);
+int bosip_b200_tv(bosip_b200_ctx* ctx, const double* log_ws, const double* a, const double* t, int64_t G, int mem,
+                  double* tv_out);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------------- */
+/* FP64 pipe microbenchmark on this GPU: DMMA (mma.sync m8n8k4.f64) and DFMA TFLOP/s -- the roofline
+ * denominators MEASURED_PEAKS.json lacks. */
+int bosip_b200_fp64_peak(bosip_b200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+/* Per-kernel device time (CUDA events on the launching stream) accumulated since the last reset:
+ * ms_out[0]=cross-kernel+mean, [1]=variance GEMM, [2]=epilogue/argmax, launches_out[0..2] the launch counts. */
+int bosip_b200_timing_reset(bosip_b200_ctx* ctx, int enable);
+int bosip_b200_timing_get(bosip_b200_ctx* ctx, double* ms_out3, int64_t* launches_out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOSIP_B200_H */
