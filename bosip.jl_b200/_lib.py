@@ -56,6 +56,9 @@ PROTOTYPES = {
     "bosip_b200_gp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bosip_b200_posterior_eval": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
                                             C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p]),
+    "bosip_b200_normal_likelihood_eval": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.c_void_p, C.c_void_p, C.c_int64,
+                                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, c_int64_p]),
     "bosip_b200_acq_argmax": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.POINTER(CandSrc), C.c_int64,
                                         C.c_int64, C.c_int, c_int64_p, c_double_p, c_double_p]),
     "bosip_b200_candidates": (C.c_int, [C.c_void_p, C.POINTER(CandSrc), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),

@@ -385,17 +385,91 @@ def _closure(post, like, prior, want, key, transform=None):
     return f
 
 
-# likelihood-level closures (no prior): src/posterior/likelihood.jl:19-59
-def log_approx_likelihood(like: NormalLikelihood, post: B200GPPosterior):
-    return _closure(post, like, None, L.WANT_APPROX, "log_approx_post")
+# ----------------------------------------------------------------------------------------------- Likelihood API layer
+_LIKE_OUTS = ("loglike_marginal", "loglike", "log_marginal_mean", "log_like_mean", "log_sq_like_mean", "log_like_var")
 
 
-def log_likelihood_mean(like: NormalLikelihood, post: B200GPPosterior):
-    return _closure(post, like, None, L.WANT_MEAN, "log_post_mean")
+def normal_likelihood_eval(like: NormalLikelihood, mu, var=None, outputs=_LIKE_OUTS, ctx: Optional[Context] = None):
+    """NormalLikelihood algebra on the device for ANY ModelPosterior's (mu, var): p (vector) or p x M (matrix) inputs.
+    Returns a dict with the requested outputs (marginal ones p / p x M, the others scalar / length M) + 'n_clamped'."""
+    ctx = ctx or default_context()
+    p = len(like.z_obs)
+    vec = (np.ndim(mu) == 1) if not _is_torch(mu) else (mu.dim() == 1)
+    mu_m = mu.reshape(p, 1) if vec else mu
+    kmu, pmu, mem, M = _colmajor(mu_m, p)
+    kvar = pvar = None
+    if var is not None:
+        var_m = var.reshape(p, 1) if vec else var
+        kvar, pvar, mem2, _ = _colmajor(var_m, p)
+        if mem2 != mem:
+            raise ValueError("mu and var must live in the same memory space")
+    res, ptrs = {}, []
+    for name in _LIKE_OUTS:
+        if name in outputs:
+            shape = (p, M) if name in ("loglike_marginal", "log_marginal_mean") else (M,)
+            o, addr = _out(shape, mem, kmu); res[name] = o; ptrs.append(addr)
+        else:
+            ptrs.append(None)
+    ncl = C.c_int64(0); lk = like._c()
+    ctx._check(ctx.lib.bosip_b200_normal_likelihood_eval(ctx.h, C.byref(lk), pmu, pvar, M, mem, *ptrs, C.byref(ncl)))
+    if vec:
+        res = {k: (v[:, 0] if v.ndim == 2 else float(v[0])) for k, v in res.items()}
+    res["n_clamped"] = ncl.value
+    return res
 
 
-def log_likelihood_variance(like: NormalLikelihood, post: B200GPPosterior):
-    return _closure(post, like, None, L.WANT_VAR, "log_post_var")
+def loglike_marginal(like: NormalLikelihood, Y, x=None):
+    """src/likelihoods/normal.jl:28-30 + matrix fallback src/types/likelihood.jl:53-54"""
+    return normal_likelihood_eval(like, Y, None, ("loglike_marginal",))["loglike_marginal"]
+
+
+def loglike(like: NormalLikelihood, Y, x=None):
+    """src/types/likelihood.jl:66-71"""
+    return normal_likelihood_eval(like, Y, None, ("loglike",))["loglike"]
+
+
+def _generic(like, post, out_name, need_var):
+    """Closure over an arbitrary ModelPosterior (anything with mean(X) / var(X), e.g. the reference's MockModelPosterior)."""
+    def f(X):
+        mu = post.mean(X)
+        var = post.var(X) if need_var else None
+        return normal_likelihood_eval(like, mu, var, (out_name,))[out_name]
+    return f
+
+
+def log_approx_marginal_likelihood(like: NormalLikelihood, post):
+    """src/posterior/likelihood.jl:6-16"""
+    return _generic(like, post, "loglike_marginal", False)
+
+
+def log_marginal_likelihood_mean(like: NormalLikelihood, post):
+    """src/likelihoods/normal.jl:32-53"""
+    return _generic(like, post, "log_marginal_mean", True)
+
+
+def log_sq_likelihood_mean(like: NormalLikelihood, post):
+    """src/likelihoods/normal.jl:55-79"""
+    return _generic(like, post, "log_sq_like_mean", True)
+
+
+# likelihood-level closures (no prior): src/posterior/likelihood.jl:19-59.  A device-backed GP posterior takes the fused
+# path (one ccall per X); any other ModelPosterior goes through its own mean/var and the Likelihood-API kernel.
+def log_approx_likelihood(like: NormalLikelihood, post):
+    if isinstance(post, B200GPPosterior):
+        return _closure(post, like, None, L.WANT_APPROX, "log_approx_post")
+    return _generic(like, post, "loglike", False)
+
+
+def log_likelihood_mean(like: NormalLikelihood, post):
+    if isinstance(post, B200GPPosterior):
+        return _closure(post, like, None, L.WANT_MEAN, "log_post_mean")
+    return _generic(like, post, "log_like_mean", True)
+
+
+def log_likelihood_variance(like: NormalLikelihood, post):
+    if isinstance(post, B200GPPosterior):
+        return _closure(post, like, None, L.WANT_VAR, "log_post_var")
+    return _generic(like, post, "log_like_var", True)
 
 
 # posterior-level closures: src/posterior/log_posterior.jl:15-61

@@ -456,6 +456,67 @@ int bosip_b200_posterior_eval(bosip_b200_gp* gh, const bosip_b200_like_normal* l
   return rc;
 }
 
+int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* h, const bosip_b200_like_normal* like, const double* mu, const double* var,
+                                      int64_t M, int mem, double* marg_approx, double* l_approx, double* marg_mean,
+                                      double* l_mean, double* l_sq, double* l_var, int64_t* n_clamped) {
+  API_LOCK(h);
+  if (!like || !like->z_obs || !like->std_obs || like->p < 1 || like->p > MAX_P) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad likelihood");
+  if (M < 0 || (!mu && M > 0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "mu is required");
+  if (n_clamped) *n_clamped = 0;
+  if (M == 0) return 0;
+  const int p = like->p;
+  EpiParams ep; memset(&ep, 0, sizeof(ep));
+  ep.p = p;
+  double logc = 0.0;
+  for (int j = 0; j < p; ++j) {
+    if (!(like->std_obs[j] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "std_obs must be > 0");
+    ep.z[j] = like->z_obs[j]; ep.so[j] = like->std_obs[j];
+    logc += log(2.0 * sqrt(M_PI) * like->std_obs[j]);
+  }
+  ep.log_C = -logc;
+  cudaStream_t st = ctx->s_comp;
+  const bool host = mem == BOSIP_B200_HOST;
+  const size_t pm = (size_t)p * M, mm = (size_t)M;
+  size_t off = 0;
+  auto carve = [&](size_t n) { size_t o = off; off += (n * 8 + 255) / 256 * 256; return o; };
+  const size_t o_cnt = carve(4);
+  size_t o_mu = 0, o_var = 0, o_ma = 0, o_la = 0, o_mm = 0, o_lm = 0, o_ls = 0, o_lv = 0;
+  if (host) {
+    o_mu = carve(pm); if (var) o_var = carve(pm);
+    if (marg_approx) o_ma = carve(pm); if (l_approx) o_la = carve(mm); if (marg_mean) o_mm = carve(pm);
+    if (l_mean) o_lm = carve(mm); if (l_sq) o_ls = carve(mm); if (l_var) o_lv = carve(mm);
+  }
+  BOSIP_TRY(ensure_ws(ctx, off));
+  auto D = [&](size_t o) { return reinterpret_cast<double*>(ctx->ws + o); };
+  unsigned long long init[2] = {0ull, ~0ull};
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_cnt), init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const double *dmu = mu, *dvar = var;
+  double *dma = marg_approx, *dla = l_approx, *dmm = marg_mean, *dlm = l_mean, *dls = l_sq, *dlv = l_var;
+  if (host) {
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_mu), mu, pm * 8, cudaMemcpyHostToDevice, st)); dmu = D(o_mu);
+    if (var) { BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_var), var, pm * 8, cudaMemcpyHostToDevice, st)); dvar = D(o_var); }
+    if (marg_approx) dma = D(o_ma); if (l_approx) dla = D(o_la); if (marg_mean) dmm = D(o_mm);
+    if (l_mean) dlm = D(o_lm); if (l_sq) dls = D(o_ls); if (l_var) dlv = D(o_lv);
+  }
+  BOSIP_TRY(launch_like_eval(ctx, ep, dmu, dvar, M, dma, dla, dmm, dlm, dls, dlv, reinterpret_cast<unsigned long long*>(D(o_cnt)), st));
+  if (host) {
+    if (marg_approx) BOSIP_CUDA(ctx, cudaMemcpyAsync(marg_approx, dma, pm * 8, cudaMemcpyDeviceToHost, st));
+    if (l_approx) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_approx, dla, mm * 8, cudaMemcpyDeviceToHost, st));
+    if (marg_mean) BOSIP_CUDA(ctx, cudaMemcpyAsync(marg_mean, dmm, pm * 8, cudaMemcpyDeviceToHost, st));
+    if (l_mean) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_mean, dlm, mm * 8, cudaMemcpyDeviceToHost, st));
+    if (l_sq) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_sq, dls, mm * 8, cudaMemcpyDeviceToHost, st));
+    if (l_var) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_var, dlv, mm * 8, cudaMemcpyDeviceToHost, st));
+  }
+  unsigned long long res[2];
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(res, D(o_cnt), sizeof(res), cudaMemcpyDeviceToHost, st));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  if (n_clamped) *n_clamped = (int64_t)res[0];
+  if (res[1] != ~0ull)
+    BOSIP_FAIL(ctx, BOSIP_B200_EDOMAIN, "DomainError: likelihood variance below -1e-8 (src/posterior/likelihood.jl:61-65) at index " +
+                                          std::to_string((long long)res[1]));
+  return 0;
+}
+
 int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
                           const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
                           double* best_val, double* best_x) {

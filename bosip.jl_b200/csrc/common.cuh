@@ -157,6 +157,9 @@ int launch_argmax_chunk(Ctx* ctx, const double* vals, int64_t m_valid, int64_t g
                         cudaStream_t st);
 int launch_sum_chunk(Ctx* ctx, const double* log_post, const double* log_prior, int64_t m_valid, double* scratch,
                      double* accum, cudaStream_t st);
+int launch_like_eval(Ctx* ctx, const EpiParams& ep, const double* mu, const double* var, int64_t m, double* marg_approx,
+                     double* l_approx, double* marg_mean, double* l_mean, double* l_sq, double* l_var,
+                     unsigned long long* counters, cudaStream_t st);
 int launch_candidates(Ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t m, int64_t offset, double* out,
                       cudaStream_t st);
 // fit.cu

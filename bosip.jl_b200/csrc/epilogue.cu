@@ -113,6 +113,55 @@ int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* x
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ likelihood from (mu, var)
+// The Likelihood-API layer on its own, for ANY ModelPosterior's (mu, var) p x M outputs -- what the reference's unit tests
+// exercise with MockModelPosterior (test/unit/utils.jl:1-11, test/unit/test/posterior/likelihood.jl,
+// test/unit/test/likelihoods/normal.jl).  Outputs (any may be NULL): marg_approx p x M = loglike_marginal(mu),
+// l_approx M = loglike(mu), marg_mean p x M = log_marginal_likelihood_mean, l_mean M, l_sq M = log_sq_likelihood_mean,
+// l_var M = log_likelihood_variance.
+__global__ void __launch_bounds__(256)
+like_eval_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__ mu_in, const double* __restrict__ var_in,
+                 long long m_valid, double* __restrict__ marg_approx, double* __restrict__ l_approx,
+                 double* __restrict__ marg_mean, double* __restrict__ l_mean, double* __restrict__ l_sq,
+                 double* __restrict__ l_var, unsigned long long* __restrict__ counters) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= m_valid) return;
+  const int p = ep.p;
+  double plug = 0.0, lm = 0.0, lsq = 0.0;
+  for (int j = 0; j < p; ++j) {
+    const double mu = mu_in[m * p + j], var = var_in ? var_in[m * p + j] : 0.0;
+    const double z = ep.z[j], so = ep.so[j], so2 = so * so;
+    const double t0 = normlogpdf(mu, so, z);
+    const double t1 = normlogpdf(mu, sqrt(so2 + var), z);
+    const double t2 = normlogpdf(mu, sqrt((so2 + 2.0 * var) / 2.0), z);
+    if (marg_approx) marg_approx[m * p + j] = t0;
+    if (marg_mean) marg_mean[m * p + j] = t1;
+    plug += t0; lm += t1; lsq += t2;
+  }
+  if (l_approx) l_approx[m] = plug;
+  if (l_mean) l_mean[m] = lm;
+  const double log_sq = ep.log_C + lsq;
+  if (l_sq) l_sq[m] = log_sq;
+  if (l_var) {
+    double v = exp(log_sq) - exp(2.0 * lm);
+    if (v < 0.0) {
+      if (v >= -MAX_NEG_VAR) { v = 0.0; atomicAdd(&counters[0], 1ull); }
+      else atomicMin(&counters[1], (unsigned long long)m);
+    }
+    l_var[m] = log(v);
+  }
+}
+
+int launch_like_eval(Ctx* ctx, const EpiParams& ep, const double* mu, const double* var, int64_t m, double* marg_approx,
+                     double* l_approx, double* marg_mean, double* l_mean, double* l_sq, double* l_var,
+                     unsigned long long* counters, cudaStream_t st) {
+  if (m <= 0) return 0;
+  like_eval_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ep, mu, var, (long long)m, marg_approx, l_approx, marg_mean,
+                                                               l_mean, l_sq, l_var, counters);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ argmax
 // Julia `argmax` semantics of BOSS's candidate maximisers: first maximal index; NaN never wins here.
 struct Best { double v; long long i; };

@@ -147,6 +147,18 @@ int bosip_b200_posterior_eval(bosip_b200_gp* gp, const bosip_b200_like_normal* l
                               double* log_approx_post, double* log_post_mean, double* log_post_var,
                               int64_t* n_clamped);
 
+/* ---- the Likelihood API on its own, for ANY ModelPosterior's outputs: NormalLikelihood given mu, var (p x M each;
+ *      var == NULL means zero variance).  Replaces loglike_marginal / loglike (src/likelihoods/normal.jl:28-30,
+ *      src/types/likelihood.jl:53-71), log_marginal_likelihood_mean (normal.jl:32-53), log_likelihood_mean
+ *      (src/posterior/likelihood.jl:34-43), log_sq_likelihood_mean (normal.jl:55-79), log_likelihood_variance
+ *      (src/posterior/likelihood.jl:47-59).  This is the seam the reference's unit tests use with MockModelPosterior
+ *      (test/unit/utils.jl:1-11).  Any output may be NULL. --------------------------------------------------- */
+int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* ctx, const bosip_b200_like_normal* like, const double* mu,
+                                      const double* var, int64_t M, int mem, double* loglike_marginal /* p x M */,
+                                      double* loglike /* M */, double* log_marginal_mean /* p x M */,
+                                      double* log_like_mean /* M */, double* log_sq_like_mean /* M */,
+                                      double* log_like_var /* M */, int64_t* n_clamped);
+
 /* ---- acquisition over a candidate set + argmax: MaxVar / LogMaxVar closure (src/acquisitions/maxvar.jl:9-11,
  *      logmaxvar.jl:13-15) evaluated by BOSS's SamplingAM / GridAM (docs/src/hyperparams.md:69). ----------- */
 /* Candidates index_offset .. index_offset+M-1 of the source (so that ranks can shard one global set).

@@ -257,13 +257,13 @@ def log_prior(prior: ProductPrior, X):
         x = X[k]
         kind, prm = prior.kind[k], prior.params[k]
         if kind == UNIFORM:
-            a, b = prm
+            a, b = prm[:2]
             t = np.where((x >= a) & (x <= b), -math.log(b - a), -np.inf)
         elif kind == NORMAL:
-            m, s = prm
+            m, s = prm[:2]
             t = normlogpdf(m, s, x)
         elif kind == TRUNCNORMAL:
-            m, s, a, b = prm
+            m, s, a, b = prm[:4]
             t = np.where((x >= a) & (x <= b), normlogpdf(m, s, x) - truncnormal_logtp(m, s, a, b), -np.inf)
         else:
             raise ValueError(kind)

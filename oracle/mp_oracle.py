@@ -80,15 +80,15 @@ def log_prior(kind, params, x):
         xk = mp.mpf(xk)
         prm = [mp.mpf(v) for v in params[k]]
         if kind[k] == 0:
-            a, b = prm
+            a, b = prm[:2]
             if not (a <= xk <= b):
                 return mp.mpf("-inf")
             lp -= mp.log(b - a)
         elif kind[k] == 1:
-            m, s = prm
+            m, s = prm[:2]
             lp += normlogpdf(m, s, xk)
         else:
-            m, s, a, b = prm
+            m, s, a, b = prm[:4]
             if not (a <= xk <= b):
                 return mp.mpf("-inf")
             lp += normlogpdf(m, s, xk) - mp.log(mp.ncdf((b - m) / s) - mp.ncdf((a - m) / s))

@@ -1,0 +1,278 @@
+"""GPU: the CUDA path through the C ABI vs the oracle on seeded inputs, the mpmath goldens, and the edge cases
+(ragged sizes, chunk boundaries, every kernel/prior kind, options, device-resident buffers, error behaviour)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bosip_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-10  # BASELINE.json north_star: 1e-10 relative error in Float64
+
+
+def problem(bb, name="C2", **kw):
+    pr = bb.synth.make_problem(name, **kw)
+    model = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma)
+    like = bb.NormalLikelihood(pr.z_obs, pr.std_obs)
+    prior = bb.ProductPrior(pr.prior_kind, pr.prior_params)
+    ofit = orc.gp_fit(pr.kernel_id, pr.X, pr.Y, pr.lam, pr.alpha, pr.sigma)
+    olike = orc.NormalLikelihood(pr.z_obs, pr.std_obs)
+    oprior = orc.ProductPrior(list(pr.prior_kind), [list(q) for q in pr.prior_params])
+    return pr, model, like, prior, ofit, olike, oprior
+
+
+def queries(pr, M, seed=0, spill=0.2):
+    """Uniform in a box slightly larger than the domain, so that some points fall outside the prior support."""
+    rng = np.random.default_rng(seed)
+    w = (pr.ub - pr.lb)[:, None]
+    return rng.uniform(pr.lb[:, None] - spill * w, pr.ub[:, None] + spill * w, size=(pr.d, M))
+
+
+def assert_mu(mu, omu):
+    scale = np.max(np.abs(omu))
+    assert np.max(np.abs(mu - omu) / (np.abs(omu) + 1e-3 * scale)) < TOL
+
+
+def assert_var(var, ovar, kxx):
+    # 1e-10 relative where the variance is not dominated by the cancellation alpha^2 - ||v||^2
+    assert np.max(np.abs(var - ovar) / (np.abs(ovar) + 1e-3 * kxx[:, None])) < TOL
+
+
+def assert_logs(res, ores):
+    for k in ("log_approx_post", "log_post_mean"):
+        a, b = res[k], ores[k]
+        fin = np.isfinite(b)
+        np.testing.assert_array_equal(np.isneginf(a), np.isneginf(b))
+        np.testing.assert_allclose(a[fin], b[fin], rtol=TOL)
+    a, b = res["log_post_var"], ores["log_post_var"]
+    # log V = log(E[l^2] - E[l]^2) is computed in linear space like the reference; errors are amplified by
+    # amp = (E[l^2] + E[l]^2)/V, so the gate is 1e-10 relative + eps-level * amp
+    mu, var = ores["mu"], ores["var"]
+    fin = np.isfinite(b) & np.isfinite(a)
+    assert np.sum(np.isfinite(a) != np.isfinite(b)) <= 1e-3 * a.size + 1  # V rounds to 0 on one side only at the underflow edge
+    err = np.abs(a[fin] - b[fin])
+    assert np.all(err <= TOL * np.abs(b[fin]) + 1e-7)
+    if err.size:
+        assert np.median(err / np.abs(b[fin])) < 1e-12
+
+
+@pytest.mark.parametrize("name,M", [("C1", 10201), ("C2", 30000), ("C3", 20000)])
+def test_fit_predict_and_closures_vs_oracle(bb, ctx, name, M):
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, name)
+    Xq = bb.synth.grid_queries(pr.lb, pr.ub, 101) if name == "C1" else queries(pr, M)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    Lg, Lig, ag = post.factors()
+    assert np.max(np.abs(Lg - ofit.L)) / np.max(np.abs(ofit.L)) < 1e-12
+    assert np.max(np.abs(ag - ofit.a)) / np.max(np.abs(ofit.a)) < 1e-9   # kappa(K) * eps
+    for j in range(pr.p):
+        assert np.max(np.abs(Lig[j] @ ofit.L[j] - np.eye(pr.N))) < 1e-11
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    mu, var = post.mean_and_var(Xq)
+    assert mu.shape == (pr.p, Xq.shape[1]) and var.shape == mu.shape          # p x M like test/unit/utils.jl:8-11
+    assert_mu(mu, omu); assert_var(var, ovar, pr.alpha ** 2)
+    np.testing.assert_allclose(post.mean(Xq), mu, rtol=0, atol=0)              # mean-only path is bit-identical
+    np.testing.assert_allclose(post.mean_and_std(Xq)[1], np.sqrt(var), rtol=1e-15)
+    v1 = post.mean_and_var(Xq[:, 7])                                            # vector method -> length p
+    assert v1[0].shape == (pr.p,) and np.array_equal(v1[0], mu[:, 7]) and np.array_equal(v1[1], var[:, 7])
+    res = bb.posterior_eval(post, like, prior, Xq, 7)
+    ores = orc.posterior_eval(ofit, olike, oprior, Xq)
+    assert_logs(res, ores)
+    assert np.isneginf(res["log_approx_post"]).sum() == np.isneginf(ores["log_prior"]).sum()
+
+
+@pytest.mark.parametrize("name,M", [("C2", 5000), ("C3", 5000)])
+def test_host_factors_exact_parity_mode(bb, ctx, name, M):
+    """Evaluator parity with the SAME factors as the oracle (bosip_b200_gp_load_factors): kappa-free 1e-10 gate."""
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, name)
+    Xq = queries(pr, M, seed=3)
+    post = bb.model_posterior_from_factors(model, pr.X, ofit.L, ofit.a, ctx=ctx)
+    mu, var = post.mean_and_var(Xq)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    assert_mu(mu, omu); assert_var(var, ovar, pr.alpha ** 2)
+    assert_logs(bb.posterior_eval(post, like, prior, Xq, 7), orc.posterior_eval(ofit, olike, oprior, Xq))
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_mpmath_goldens(bb, ctx, ci):
+    c = json.load(open(os.path.join(GOLD, "gp_small.json")))["cases"][ci]
+    X, Y, Xq = np.array(c["X"]), np.array(c["Y"]), np.array(c["Xq"])
+    model = bb.GaussianProcess(c["kernel_id"], np.array(c["lam"]), np.array(c["alpha"]), np.array(c["sigma"]), clamp_var=False)
+    post = bb.model_posterior(model, X, Y, ctx=ctx)
+    like = bb.NormalLikelihood(c["z_obs"], c["std_obs"])
+    mu, var = post.mean_and_var(Xq)
+    a2 = np.array(c["alpha"]) ** 2
+    for name, prd in c["priors"].items():
+        prior = bb.ProductPrior(prd["kind"], prd["params"])
+        res = bb.posterior_eval(post, like, prior, Xq, 7)
+        for i, pt in enumerate(c["points"]):
+            np.testing.assert_allclose(mu[:, i], pt["mu"], rtol=TOL, atol=1e-12)
+            np.testing.assert_allclose(var[:, i], pt["var"], rtol=TOL, atol=1e-12 * a2.max())
+            lp = pt["log_prior"][name]
+            if math.isinf(lp):
+                assert res["log_approx_post"][i] == -np.inf and res["log_post_mean"][i] == -np.inf and res["log_post_var"][i] == -np.inf
+                continue
+            assert res["log_approx_post"][i] == pytest.approx(lp + pt["loglike"], rel=TOL)
+            assert res["log_post_mean"][i] == pytest.approx(lp + pt["log_like_mean"], rel=TOL)
+            amp = math.exp(pt["log_sq_like_mean"]) / max(pt["like_var"], 1e-300)
+            assert res["log_post_var"][i] == pytest.approx(2 * lp + pt["log_like_var"], abs=1e-11 * amp + 1e-9)
+
+
+@pytest.mark.parametrize("kernel_id", [0, 1, 2])
+@pytest.mark.parametrize("d,p,N,M", [(1, 1, 1, 1), (3, 2, 63, 127), (3, 2, 64, 128), (4, 3, 65, 129), (6, 1, 130, 1000),
+                                      (7, 2, 257, 513), (12, 1, 100, 300), (20, 1, 48, 77)])
+def test_ragged_shapes_and_kernels(bb, ctx, kernel_id, d, p, N, M):
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, "X", d=d, p=p, N=N, kernel_id=kernel_id, seed=1000 + 31 * d + N)
+    Xq = queries(pr, M, seed=N, spill=0.2 if d <= 4 else 0.01)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    mu, var = post.mean_and_var(Xq)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    assert_mu(mu, omu); assert_var(var, ovar, pr.alpha ** 2)
+    assert_logs(bb.posterior_eval(post, like, prior, Xq, 7), orc.posterior_eval(ofit, olike, oprior, Xq))
+
+
+def test_chunking_is_invisible(bb, ctx):
+    """Results are bit-identical whatever the internal chunk size, and for host vs device-resident buffers."""
+    import torch
+    pr, model, like, prior, *_ = problem(bb, "C2")
+    Xq = queries(pr, 3001, seed=9)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    ref = bb.posterior_eval(post, like, prior, Xq, 7)
+    try:
+        for chunk in (128, 256, 1000):
+            ctx.set_chunk(chunk)
+            r = bb.posterior_eval(post, like, prior, Xq, 7)
+            for k in ("log_approx_post", "log_post_mean", "log_post_var"):
+                np.testing.assert_array_equal(r[k], ref[k])
+            mu, var = post.mean_and_var(Xq)
+            np.testing.assert_array_equal(mu, post.mean(Xq))
+    finally:
+        ctx.set_chunk(0)
+    Xd = torch.as_tensor(np.ascontiguousarray(Xq.T), device="cuda").t()
+    rd = bb.posterior_eval(post, like, prior, Xd, 7)
+    for k in ("log_approx_post", "log_post_mean", "log_post_var"):
+        assert rd[k].is_cuda
+        np.testing.assert_array_equal(rd[k].cpu().numpy(), ref[k])
+    mud, vard = post.mean_and_var(Xd)
+    mu, var = post.mean_and_var(Xq)
+    np.testing.assert_array_equal(mud.cpu().numpy(), mu); np.testing.assert_array_equal(vard.cpu().numpy(), var)
+    # want-subsets agree with the full call
+    for want, key in ((1, "log_approx_post"), (2, "log_post_mean"), (4, "log_post_var")):
+        np.testing.assert_array_equal(bb.posterior_eval(post, like, prior, Xq, want)[key], ref[key])
+
+
+def test_options_priors_and_mean_function(bb, ctx):
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, "C2")
+    Xq = queries(pr, 2000, seed=4)
+    # pred_noise + jitter + no clamp
+    m2 = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma, jitter=1e-6, pred_noise=True, clamp_var=False)
+    o2 = orc.gp_fit(pr.kernel_id, pr.X, pr.Y, pr.lam, pr.alpha, pr.sigma, opts=orc.GPOpts(1e-6, True, False))
+    mu, var = bb.model_posterior(m2, pr.X, pr.Y, ctx=ctx).mean_and_var(Xq)
+    omu, ovar = orc.gp_predict(o2, Xq)
+    assert_mu(mu, omu); assert_var(var, ovar, pr.alpha ** 2)
+    # prior mean function m_j(x)
+    mean_fn = lambda X: np.stack([0.3 * X[0] - 0.1, np.cos(X[1])])
+    m3 = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma, mean=mean_fn)
+    o3 = orc.gp_fit(pr.kernel_id, pr.X, pr.Y, pr.lam, pr.alpha, pr.sigma, mean_at_X=mean_fn(pr.X))
+    mu3 = bb.model_posterior(m3, pr.X, pr.Y, ctx=ctx).mean(Xq)
+    assert_mu(mu3, orc.gp_predict(o3, Xq, mean_at_Xq=mean_fn(Xq), want_var=False))
+    # uniform / normal / mixed priors and host-supplied log-prior values
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    for kinds, prms in (([0, 0], [[-5, 5], [-4, 6]]), ([1, 1], [[0.5, 2.0], [-1.0, 3.0]]), ([2, 0], [[0, 2, -5, 5], [-5, 5]])):
+        a = bb.posterior_eval(post, like, bb.ProductPrior(kinds, prms), Xq, 7)
+        b = orc.posterior_eval(ofit, olike, orc.ProductPrior(kinds, prms), Xq)
+        assert_logs(a, b)
+        c = bb.posterior_eval(post, like, None, Xq, 7, logprior=b["log_prior"])
+        assert_logs(c, b)
+    # no prior at all == the likelihood-level closures
+    nl = bb.posterior_eval(post, like, None, Xq, 7)
+    np.testing.assert_array_equal(bb.log_likelihood_variance(like, post)(Xq), nl["log_post_var"])
+    np.testing.assert_array_equal(bb.log_approx_likelihood(like, post)(Xq), nl["log_approx_post"])
+
+
+def test_closures_normalisation_and_evidence(bb, ctx):
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, "C2")
+    prob = bb.BosipProblem(pr.X, pr.Y, model, like, prior, (pr.lb, pr.ub), ctx)
+    Xq = queries(pr, 500, seed=2, spill=0.0)
+    ores = orc.posterior_eval(ofit, olike, oprior, Xq)
+    np.testing.assert_allclose(bb.approx_posterior(prob)(Xq), np.exp(ores["log_approx_post"]), rtol=1e-9)
+    np.testing.assert_allclose(bb.posterior_mean(prob)(Xq), np.exp(ores["log_post_mean"]), rtol=1e-9)
+    np.testing.assert_allclose(bb.posterior_variance(prob)(Xq), np.exp(ores["log_post_var"]), rtol=1e-6)
+    assert isinstance(bb.log_posterior_mean(prob)(Xq[:, 3]), float)            # vector method -> Real
+    xs = prior.rand(10_000, np.random.default_rng(1))                           # evidence.jl:21
+    oxs = orc.posterior_eval(ofit, olike, oprior, xs)
+    for which, key in (("approx", "log_approx_post"), ("mean", "log_post_mean")):
+        ev = bb.evidence(prob, which, xs=xs)
+        assert ev == pytest.approx(orc.evidence(oxs[key], oxs["log_prior"]), rel=1e-10)
+    ev = bb.evidence(prob, "mean", xs=xs)
+    np.testing.assert_allclose(bb.posterior_mean(prob, normalize=True, xs=xs)(Xq), np.exp(ores["log_post_mean"] - math.log(ev)), rtol=1e-9)
+    np.testing.assert_allclose(bb.posterior_variance(prob, normalize=True, xs=xs)(Xq), np.exp(ores["log_post_var"] - 2 * math.log(ev)), rtol=1e-6)
+
+
+def test_argmax_matches_oracle_ties_and_sources(bb, ctx):
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, "C2")
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    Xq = queries(pr, 40000, seed=11, spill=0.05)
+    ores = orc.posterior_eval(ofit, olike, oprior, Xq)
+    top2 = np.sort(ores["log_post_var"][np.isfinite(ores["log_post_var"])])[-2:]
+    assert top2[1] - top2[0] > 1e-9 * abs(top2[1]), "regenerate: not tie-free"
+    for acq, logspace in ((bb.LogMaxVar(), True), (bb.MaxVar(), False)):
+        oi, ov = orc.maxvar_argmax(ores["log_post_var"], logspace)
+        bi, bv, bx = bb.acq_argmax(post, like, prior, acq, bb.CandidateSource.from_points(Xq))
+        assert bi == oi and bv == pytest.approx(ov, rel=1e-9)
+        np.testing.assert_array_equal(bx, Xq[:, oi])
+    # duplicated winner -> first index (Julia argmax); offset labels global indices
+    Xt = np.concatenate([Xq[:, :100], Xq[:, [oi]], Xq[:, 100:200], Xq[:, [oi]]], axis=1)
+    bi, _, _ = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(Xt))
+    assert bi == 100
+    # every candidate outside the prior support -> no winner
+    far = np.full((2, 300), 9.0)
+    bi, bv, _ = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(far))
+    assert bi == -1 and bv == -np.inf
+    # device-generated candidates == host Philox mirror == explicit points, and sharded ranges compose
+    src = bb.CandidateSource.philox(20261019, pr.lb, pr.ub, 50000)
+    cand = bb.synth.philox_uniform_candidates(20261019, 0, 50000, pr.lb, pr.ub)
+    np.testing.assert_array_equal(bb.candidates(ctx, src, 0, 50000), cand)
+    full = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), src)
+    pts = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(cand))
+    assert full[0] == pts[0] and full[1] == pts[1]
+    np.testing.assert_array_equal(full[2], cand[:, full[0]])
+    shards = [bb.acq_argmax(post, like, prior, bb.LogMaxVar(), src, *bb.parallel.shard_range(50000, r, 8)) for r in range(8)]
+    w = bb.parallel.combine_argmax(np.array([s[1] for s in shards]), np.array([s[0] for s in shards]))
+    assert shards[w][0] == full[0] and shards[w][1] == full[1]
+    # grid source (C1: 101 x 101, examples/simple/main.jl:69) == explicit grid
+    gsrc = bb.CandidateSource.grid(pr.lb, pr.ub, 101)
+    G = bb.synth.grid_queries(pr.lb, pr.ub, 101)
+    np.testing.assert_array_equal(bb.candidates(ctx, gsrc, 0, 10201), G)
+    a = bb.acq_argmax(post, like, prior, bb.MaxVar(), gsrc); b = bb.acq_argmax(post, like, prior, bb.MaxVar(), bb.CandidateSource.from_points(G))
+    assert a[0] == b[0] and a[1] == b[1]
+    # the maximiser object (single process: identity exchange)
+    prob = bb.BosipProblem(pr.X, pr.Y, model, like, prior, (pr.lb, pr.ub), ctx)
+    x, val = bb.B200CandidateAM(src).maximize_acquisition(prob, bb.LogMaxVar())
+    np.testing.assert_array_equal(x, full[2]); assert val == full[1]
+
+
+def test_error_behaviour(bb, ctx):
+    pr, model, like, prior, *_ = problem(bb, "C1")
+    # duplicate training points with zero noise: not positive definite -> PosDefException (Julia cholesky)
+    Xd = np.concatenate([pr.X, pr.X[:, :1]], axis=1); Yd = np.concatenate([pr.Y, pr.Y[:, :1]], axis=1)
+    with pytest.raises(bb.PosDefException):
+        bb.model_posterior(bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, 0.0 * pr.sigma), Xd, Yd, ctx=ctx)
+    with pytest.raises(bb.BosipB200Error) as e:
+        bb.model_posterior(bb.GaussianProcess(7, pr.lam, pr.alpha, pr.sigma), pr.X, pr.Y, ctx=ctx)
+    assert e.value.code == bb._lib.EINVAL
+    with pytest.raises(bb.BosipB200Error):
+        bb.model_posterior(bb.GaussianProcess(pr.kernel_id, -pr.lam, pr.alpha, pr.sigma), pr.X, pr.Y, ctx=ctx)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    with pytest.raises(bb.BosipB200Error):  # p mismatch between likelihood and GP
+        bb.posterior_eval(post, bb.NormalLikelihood([0.0, 1.0], [1.0, 1.0]), prior, pr.X, 7)
+    with pytest.raises(bb.BosipB200Error):  # std_obs must be positive
+        bb.posterior_eval(post, bb.NormalLikelihood([0.0], [0.0]), prior, pr.X, 7)
+    with pytest.raises(ValueError):         # wrong input dimension
+        post.mean(np.zeros((3, 4)))
+    # the context stays usable after errors, and an empty batch is a no-op
+    assert post.mean(pr.X).shape == (1, pr.N)
+    assert post.mean(np.zeros((2, 0))).shape == (1, 0)

@@ -1,0 +1,166 @@
+"""CPU: the C-ABI library loads and exports every symbol include/bosip_b200.h declares (no compute calls without a GPU),
+the host logic (sharding, argmax / log-sum-exp combination, Philox mirror, synthetic generators), and the N>1 exchange
+steps over gloo with world_size 2."""
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_header_symbol(bb):
+    hdr = open(os.path.join(ROOT, "include", "bosip_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bosip_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = bb._lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(bb._lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert lib.bosip_b200_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu(bb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(bb.BosipB200Error) as e:
+        bb.Context(0)
+    assert e.value.code == bb._lib.ECUDA and "no CPU path" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bosip.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_shard_range_partitions(bb):
+    for total in (0, 1, 7, 100, 10 ** 8 + 3):
+        for world in (1, 2, 3, 8):
+            parts = [bb.parallel.shard_range(total, r, world) for r in range(world)]
+            assert sum(c for _, c in parts) == total
+            pos = 0
+            for s, c in parts:
+                assert s == pos
+                pos += c
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_combine_argmax_semantics(bb):
+    f = bb.parallel.combine_argmax
+    assert f(np.array([1.0, 3.0, 2.0]), np.array([5, 9, 1])) == 1
+    assert f(np.array([3.0, 3.0]), np.array([9, 4])) == 1            # tie -> lowest global index (Julia argmax)
+    assert f(np.array([np.nan, -np.inf]), np.array([0, 7])) == 1      # NaN never wins
+    assert f(np.array([0.0, 0.0]), np.array([-1, -1])) == -1          # no candidate anywhere
+
+
+def test_lse_merge(bb):
+    rng = np.random.default_rng(1)
+    v = rng.normal(0, 30, 1000)
+    M, S = -math.inf, 0.0
+    for chunk in np.array_split(v, 7):
+        m = chunk.max(); s = np.exp(chunk - m).sum()
+        M, S = bb.parallel.lse_merge(M, S, m, s)
+    ref = v.max() + math.log(np.exp(v - v.max()).sum())
+    assert M + math.log(S) == pytest.approx(ref, rel=1e-14)
+    assert bb.parallel.lse_merge(-math.inf, 0.0, -math.inf, 0.0) == (-math.inf, 0.0)
+
+
+def test_philox_known_answer_and_determinism(bb):
+    s = bb.synth
+    # Random123 known-answer vector for philox4x32-10: ctr = 0, key = 0
+    r = s.philox4x32(np.zeros((1, 4), np.uint32), np.zeros(2, np.uint32))[0]
+    assert [hex(int(x)) for x in r] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    r = s.philox4x32(np.full((1, 4), 0xFFFFFFFF, np.uint32), np.full(2, 0xFFFFFFFF, np.uint32))[0]
+    assert [hex(int(x)) for x in r] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    lb, ub = -5 * np.ones(5), 5 * np.ones(5)
+    a = s.philox_uniform_candidates(42, 1000, 64, lb, ub)
+    b = s.philox_uniform_candidates(42, 0, 2000, lb, ub)[:, 1000:1064]
+    np.testing.assert_array_equal(a, b)  # keyed by global index: independent of how the range is sharded
+    assert a.min() >= -5 and a.max() < 5
+    big = s.philox_uniform_candidates(7, 2 ** 33, 4, lb, ub)
+    assert np.isfinite(big).all()
+
+
+def test_synth_problems_are_seeded(bb):
+    a = bb.synth.make_problem("C2"); b = bb.synth.make_problem("C2")
+    np.testing.assert_array_equal(a.X, b.X); np.testing.assert_array_equal(a.Y, b.Y)
+    assert a.X.shape == (2, 200) and a.Y.shape == (2, 200) and a.lam.shape == (2, 2)
+    c3 = bb.synth.make_problem("C3")
+    assert (c3.d, c3.p, c3.N) == (5, 4, 1000)
+    g = bb.synth.grid_queries([-5, -5], [5, 5], 101)
+    assert g.shape == (2, 10201) and g[0, 1] == pytest.approx(-4.9) and g[1, 101] == pytest.approx(-4.9)
+
+
+def test_api_argument_marshalling(bb):
+    api = bb.api
+    X = np.arange(6.0).reshape(2, 3)
+    keep, addr, mem, n = api._colmajor(X, 2)
+    assert keep.flags.f_contiguous and n == 3 and mem == bb._lib.HOST
+    assert list(np.frombuffer(keep.tobytes(order="A"), dtype=np.float64)) == [0, 3, 1, 4, 2, 5]  # column = point
+    with pytest.raises(ValueError):
+        api._colmajor(X, 3)
+    pr = bb.ProductPrior([0, 2], [[-1, 1], [0, 1, -2, 2]])
+    assert pr.params.shape == (2, 4) and pr.d == 2
+    xs = pr.rand(100, np.random.default_rng(0))
+    assert xs.shape == (2, 100) and np.all(np.abs(xs[0]) <= 1) and np.all(np.abs(xs[1]) <= 2)
+
+
+GLOO_WORKER = r'''
+import os, sys, math
+import numpy as np
+sys.path.insert(0, os.environ["BOSIP_ROOT"])
+import torch.distributed as dist
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+import bosip_b200 as bb
+P = bb.parallel
+r, w = P.rank_world()
+assert w == 2
+# shard + argmax exchange: rank 1 holds the winner; ties resolve to the lowest global index
+start, count = P.shard_range(11)
+vals = np.array([0.1, 0.9, 0.3, 0.9, 0.2, 0.5, 0.95, 0.1, 0.95, 0.0, 0.4])
+loc = vals[start:start + count]
+i = int(np.argmax(loc))
+idx, val, x = P.argmax_allgather(start + i, float(loc[i]), np.array([float(start + i), 1.0]))
+assert (idx, val) == (6, 0.95) and x[0] == 6.0, (idx, val, x)
+idx, val, x = P.argmax_allgather(-1, -math.inf, np.zeros(2))          # nobody has a candidate
+assert idx == -1
+big = (1 << 40) + 5 + r
+idx, val, x = P.argmax_allgather(big, 1.0, np.zeros(2))                # tie -> lowest index; 64-bit indices survive
+assert idx == (1 << 40) + 5
+# sums + counts
+s = P.allreduce_sum(np.array([1.0 + r, 10.0 * (r + 1), -1.0]))
+assert list(s) == [3.0, 30.0, -2.0]
+assert P.allreduce_count(5 + r) == 11
+# log-sum-exp exchange equals the single-process value
+v = np.random.default_rng(3).normal(0, 20, 1001)
+st, ct = P.shard_range(len(v)); mine = v[st:st + ct]
+m = mine.max(); M, S = P.lse_allgather(m, float(np.exp(mine - m).sum()))
+ref = v.max() + math.log(np.exp(v - v.max()).sum())
+assert abs(M + math.log(S) - ref) < 1e-12
+# fit-input broadcast
+arrs = P.broadcast_fit_inputs({"X": np.full((2, 3), float(r)), "a": np.array([7.0 + r])})
+assert arrs["X"].sum() == 0.0 and arrs["a"][0] == 7.0
+dist.barrier(); dist.destroy_process_group()
+print("RANK_OK", r)
+'''
+
+
+def test_gloo_world_size_2_exchange_steps(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, BOSIP_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"RANK_OK {r}" in o, o
