@@ -45,6 +45,8 @@ PROTOTYPES = {
     "bosip_b200_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "bosip_b200_shutdown": (C.c_int, [C.c_void_p]),
     "bosip_b200_last_error": (C.c_char_p, [C.c_void_p]),
+    "bosip_b200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bosip_b200_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
     "bosip_b200_set_chunk": (C.c_int, [C.c_void_p, C.c_int64]),
     "bosip_b200_gp_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                     c_double_p, c_double_p, c_double_p, C.POINTER(GpOpts), C.POINTER(C.c_void_p)]),
@@ -56,6 +58,9 @@ PROTOTYPES = {
     "bosip_b200_gp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bosip_b200_posterior_eval": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
                                             C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p]),
+    "bosip_b200_posterior_eval_argmax": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
+                                                   C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p,
+                                                   C.c_int, C.c_int64, c_int64_p, c_double_p]),
     "bosip_b200_normal_likelihood_eval": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.c_void_p, C.c_void_p, C.c_int64,
                                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, c_int64_p]),

@@ -116,6 +116,15 @@ class Context:
             raise PosDefException(rc, msg)
         raise BosipB200Error(rc, msg)
 
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Launch compute kernels on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None restores."""
+        self._check(self.lib.bosip_b200_set_stream(self.h, cuda_stream))
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.bosip_b200_launch_count(self.h, C.byref(n)))
+        return n.value
+
     def set_chunk(self, max_points: int):
         self._check(self.lib.bosip_b200_set_chunk(self.h, int(max_points)))
 
@@ -346,8 +355,10 @@ def model_posterior_from_factors(model: GaussianProcess, X, L_fac, a, ctx: Optio
 
 # ----------------------------------------------------------------------------------------------- fused closures
 def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optional[ProductPrior], X, want: int,
-                   logprior=None):
-    """One fused call: returns dict of the requested length-M outputs + 'n_clamped'."""
+                   logprior=None, acq=None, index_offset: int = 0, out=None):
+    """One fused call: returns dict of the requested length-M outputs + 'n_clamped'; with `acq` (MaxVar()/LogMaxVar()) also
+    'best_idx' (index_offset + position) and 'best_val' from the same sweep.  `out` may hold preallocated output buffers
+    (dict name -> array/tensor in the same memory space as X)."""
     vec = (np.ndim(X) == 1) if not _is_torch(X) else (X.dim() == 1)
     Xm = X.reshape(post.d, 1) if vec else X
     keep, addr, mem, M = _colmajor(Xm, post.d)
@@ -366,15 +377,22 @@ def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optiona
     ptrs = []
     for bit, name in ((L.WANT_APPROX, "log_approx_post"), (L.WANT_MEAN, "log_post_mean"), (L.WANT_VAR, "log_post_var")):
         if want & bit:
-            o, p_ = _out((M,), mem, keep); outs[name] = o; ptrs.append(p_)
+            if out is not None and name in out:
+                o = out[name]; p_ = o.data_ptr() if _is_torch(o) else o.ctypes.data
+            else:
+                o, p_ = _out((M,), mem, keep)
+            outs[name] = o; ptrs.append(p_)
         else:
             ptrs.append(None)
-    ncl = C.c_int64(0)
-    post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval(post.h, C.byref(lk), C.byref(pr), addr, M, mem, maddr, want,
-                                                          ptrs[0], ptrs[1], ptrs[2], C.byref(ncl)))
+    ncl = C.c_int64(0); bi = C.c_int64(-1); bv = C.c_double(0.0)
+    post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval_argmax(
+        post.h, C.byref(lk), C.byref(pr), addr, M, mem, maddr, want, ptrs[0], ptrs[1], ptrs[2], C.byref(ncl),
+        acq.acq_id if acq is not None else -1, index_offset, C.byref(bi), C.byref(bv)))
     if vec:
         outs = {k: float(v[0]) for k, v in outs.items()}
     outs["n_clamped"] = ncl.value
+    if acq is not None:
+        outs["best_idx"], outs["best_val"] = bi.value, bv.value
     return outs
 
 

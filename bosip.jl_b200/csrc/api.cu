@@ -240,6 +240,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
       if (sw.logprior) lpin_dev = sw.logprior + c0;
     }
     // ---------------- compute
+    ctx->launches += 2 + (sw.need_var ? 1 : 0) + (gen ? 1 : 0) + (sw.do_argmax ? 2 : 0) + (sw.do_evidence ? 2 : 0);
     t_begin(ctx, 0, sc);
     BOSIP_TRY(launch_kstar(ctx, gp, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var, sc));
     t_end(ctx, sc);
@@ -334,9 +335,10 @@ int bosip_b200_init(int device, bosip_b200_ctx** out) {
   bosip_b200_ctx* h = new bosip_b200_ctx();
   Ctx* ctx = &h->c;
   ctx->device = device; ctx->sms = prop.multiProcessorCount;
-  bool ok = cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
+  bool ok = cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->s_comp = ctx->s_own;
   for (int b = 0; b < 2 && ok; ++b)
     ok = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_comp[b], cudaEventDisableTiming) == cudaSuccess &&
@@ -356,8 +358,22 @@ int bosip_b200_shutdown(bosip_b200_ctx* h) {
   for (auto& e : h->tp.pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_in[b]); cudaEventDestroy(ctx->ev_comp[b]); cudaEventDestroy(ctx->ev_out[b]); }
   cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
-  cudaStreamDestroy(ctx->s_comp); cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
+  cudaStreamDestroy(ctx->s_own); cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
   delete h;
+  return 0;
+}
+
+int bosip_b200_set_stream(bosip_b200_ctx* h, void* stream) {
+  API_LOCK(h);
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
+  ctx->s_comp = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->s_own;
+  return 0;
+}
+
+int bosip_b200_launch_count(bosip_b200_ctx* h, int64_t* out) {
+  API_LOCK(h);
+  if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
+  *out = ctx->launches;
   return 0;
 }
 
@@ -431,15 +447,19 @@ int bosip_b200_gp_predict(bosip_b200_gp* gh, const double* Xq, int64_t M, int me
   return run_sweep(ctx, sw);
 }
 
-int bosip_b200_posterior_eval(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
-                              const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
-                              double* log_approx_post, double* log_post_mean, double* log_post_var, int64_t* n_clamped) {
+int bosip_b200_posterior_eval_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                                     const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
+                                     double* log_approx_post, double* log_post_mean, double* log_post_var, int64_t* n_clamped,
+                                     int acq, int64_t index_offset, int64_t* best_idx, double* best_val) {
   if (!gh || !gh->g) return BOSIP_B200_EINVAL;
   bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
   API_LOCK(h);
   if (!like) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood is NULL");
   if (!Xq && M > 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "Xq is NULL");
-  if ((want & 7u) == 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "`want` selects no output");
+  const bool do_arg = acq >= 0;
+  if (do_arg && acq != BOSIP_B200_ACQ_MAXVAR && acq != BOSIP_B200_ACQ_LOGMAXVAR) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown acquisition");
+  if (do_arg && (!best_idx || !best_val || index_offset < 0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "argmax outputs are required");
+  if ((want & 7u) == 0 && !do_arg) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "`want` selects no output");
   if (((want & BOSIP_B200_WANT_APPROX) && !log_approx_post) || ((want & BOSIP_B200_WANT_MEAN) && !log_post_mean) ||
       ((want & BOSIP_B200_WANT_VAR) && !log_post_var))
     BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "an output selected by `want` is NULL");
@@ -448,12 +468,21 @@ int bosip_b200_posterior_eval(bosip_b200_gp* gh, const bosip_b200_like_normal* l
   sw.la = (want & BOSIP_B200_WANT_APPROX) ? log_approx_post : nullptr;
   sw.lm = (want & BOSIP_B200_WANT_MEAN) ? log_post_mean : nullptr;
   sw.lv = (want & BOSIP_B200_WANT_VAR) ? log_post_var : nullptr;
-  sw.need_var = (want & (BOSIP_B200_WANT_MEAN | BOSIP_B200_WANT_VAR)) != 0;
+  sw.need_var = do_arg || (want & (BOSIP_B200_WANT_MEAN | BOSIP_B200_WANT_VAR)) != 0;
+  sw.do_argmax = do_arg; sw.exp_vals = (acq == BOSIP_B200_ACQ_MAXVAR) ? 1 : 0; sw.index_offset = index_offset;
   BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
   if (prior && prior->logprior) sw.logprior = prior->logprior;
   int rc = run_sweep(ctx, sw);
   if (n_clamped) *n_clamped = sw.n_clamped;
+  if (do_arg) { *best_idx = sw.best_idx; *best_val = sw.best_idx >= 0 ? sw.best_val : -INFINITY; }
   return rc;
+}
+
+int bosip_b200_posterior_eval(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                              const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
+                              double* log_approx_post, double* log_post_mean, double* log_post_var, int64_t* n_clamped) {
+  return bosip_b200_posterior_eval_argmax(gh, like, prior, Xq, M, mem, mean_at_Xq, want, log_approx_post, log_post_mean,
+                                          log_post_var, n_clamped, -1, 0, nullptr, nullptr);
 }
 
 int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* h, const bosip_b200_like_normal* like, const double* mu, const double* var,

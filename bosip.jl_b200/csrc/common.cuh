@@ -66,7 +66,8 @@ struct Ctx {
   int sms = 0;
   std::mutex mu;
   std::string err;
-  cudaStream_t s_comp = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_comp = nullptr, s_own = nullptr, s_in = nullptr, s_out = nullptr;  // s_comp == s_own unless set_stream
+  int64_t launches = 0;
   cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
   int64_t user_chunk = 0;
   // chunk workspace (grown on demand)

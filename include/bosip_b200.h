@@ -110,6 +110,12 @@ int bosip_b200_init(int device, bosip_b200_ctx** out);
 int bosip_b200_shutdown(bosip_b200_ctx* ctx);
 /* Last error message of this context (ctx == NULL: of the last failed bosip_b200_init on this thread). */
 const char* bosip_b200_last_error(const bosip_b200_ctx* ctx);
+/* Launch the compute kernels on a caller-owned CUDA stream (a `cudaStream_t` passed as void*, e.g. the host framework's
+ * current stream) so that the caller's events bracket them; NULL restores the context's own stream.  The H2D/D2H
+ * staging streams stay internal.  Every entry point still returns only when its outputs are complete. */
+int bosip_b200_set_stream(bosip_b200_ctx* ctx, void* cuda_stream);
+/* Number of kernels this context has launched since creation (bench.py: gpu_launches). */
+int bosip_b200_launch_count(bosip_b200_ctx* ctx, int64_t* out);
 /* Upper bound for the number of query points processed per internal chunk (0 = library default). */
 int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
 
@@ -146,6 +152,15 @@ int bosip_b200_posterior_eval(bosip_b200_gp* gp, const bosip_b200_like_normal* l
                               const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
                               double* log_approx_post, double* log_post_mean, double* log_post_var,
                               int64_t* n_clamped);
+
+/* Same sweep, plus the acquisition argmax over the evaluated points in the same pass (acq = BOSIP_B200_ACQ_* or -1 for
+ * none): what a SamplingAM-style maximiser needs when the per-point values are wanted too.  best_idx is
+ * index_offset + (0-based position in Xq), -1 if no finite value; ties -> lowest index. */
+int bosip_b200_posterior_eval_argmax(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                                     const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
+                                     double* log_approx_post, double* log_post_mean, double* log_post_var,
+                                     int64_t* n_clamped, int acq, int64_t index_offset, int64_t* best_idx,
+                                     double* best_val);
 
 /* ---- the Likelihood API on its own, for ANY ModelPosterior's outputs: NormalLikelihood given mu, var (p x M each;
  *      var == NULL means zero variance).  Replaces loglike_marginal / loglike (src/likelihoods/normal.jl:28-30,
