@@ -143,7 +143,7 @@ struct Sweep {
 
 static int run_sweep(Ctx* ctx, Sweep& sw) {
   Gp* gp = sw.gp;
-  const int p = gp->p, d = gp->d, Ns = gp->Ns, T = gp->T;
+  const int p = gp->p, d = gp->d, Ns = gp->Ns;
   const int64_t M = sw.M;
   if (M < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "M must be >= 0");
   if (M == 0) return 0;
@@ -175,7 +175,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   auto carve = [&](size_t n_doubles) { size_t o = off; off += (n_doubles * 8 + 255) / 256 * 256; return o; };
   const size_t o_Ks = sw.need_var ? carve((size_t)p * Ns * mc) : 0;
   const size_t o_mu_part = carve((size_t)nsplit * p * mc);
-  const size_t o_q_part = sw.need_var ? carve((size_t)T * p * mc) : 0;
+  const size_t o_q_part = sw.need_var ? carve((size_t)p * mc) : 0;
   const bool stage_x = host || gen;
   size_t o_x[2] = {0, 0}, o_mean[2] = {0, 0}, o_lpin[2] = {0, 0}, o_mu[2] = {0, 0}, o_var[2] = {0, 0}, o_la[2] = {0, 0},
          o_lm[2] = {0, 0}, o_lv[2] = {0, 0}, o_lp[2] = {0, 0};

@@ -106,7 +106,7 @@ int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* x
   if (m_valid <= 0) return 0;
   const int block = 256;
   const unsigned grid = (unsigned)((m_valid + block - 1) / block);
-  epilogue_kernel<<<grid, block, 0, st>>>(ep, xq, logprior, mean_at_xq, (long long)m_valid, (long long)mc, nsplit, gp->T,
+  epilogue_kernel<<<grid, block, 0, st>>>(ep, xq, logprior, mean_at_xq, (long long)m_valid, (long long)mc, nsplit, 1 /* the GEMM writes one q per row */,
                                           mu_part, have_var ? 1 : 0, q_part, mu_out, var_out, lp_out, log_approx,
                                           log_mean, log_var, counters, (unsigned long long)index_base);
   BOSIP_CUDA(ctx, cudaGetLastError());
