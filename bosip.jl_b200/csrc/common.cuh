@@ -176,5 +176,6 @@ int tv_stage2(Ctx* ctx, const double* lw, const double* a, const double* t, int6
               double evt, double* out2);
 // peaks.cu
 int fp64_peak(Ctx* ctx, double* dmma, double* dfma);
+int math_selftest(Ctx* ctx, const double* x, int64_t n, double* e_fast, double* q_fast, double* e_ref, double* q_ref);
 
 }  // namespace bosip

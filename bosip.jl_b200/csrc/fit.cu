@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace bosip {
 
@@ -96,13 +97,6 @@ static int gemm64(Ctx* ctx, const GemmArgs& g, int M, int N, int batch, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-template <int KERNEL>
-__device__ __forceinline__ double kval(double r2) {
-  if (KERNEL == BOSIP_B200_KERNEL_SE) return exp(-r2);
-  double s = sqrt(r2);
-  if (KERNEL == BOSIP_B200_KERNEL_MATERN32) return (1.0 + s) * exp(-s);
-  return (1.0 + s + r2 * (1.0 / 3.0)) * exp(-s);
-}
 
 // Us[j][k][n] = X[k + d n] * scale[j][k]
 __global__ void scale_inputs_kernel(const double* __restrict__ X, const double* __restrict__ scale, int d, int dp, int N,
@@ -123,7 +117,7 @@ __global__ void build_K_kernel(int kernel_id, const double* __restrict__ Us, int
     const double* U = Us + (size_t)j * dp * Ns;
     double r2 = 0.0;
     for (int k = 0; k < dp; ++k) { const double t = U[(size_t)k * Ns + r] - U[(size_t)k * Ns + c]; r2 = fma(t, t, r2); }
-    double kv = kernel_id == BOSIP_B200_KERNEL_SE ? kval<0>(r2) : kernel_id == BOSIP_B200_KERNEL_MATERN32 ? kval<1>(r2) : kval<2>(r2);
+    double kv = kernel_id == BOSIP_B200_KERNEL_SE ? kernel_from_r2<0>(r2) : kernel_id == BOSIP_B200_KERNEL_MATERN32 ? kernel_from_r2<1>(r2) : kernel_from_r2<2>(r2);
     v = alpha2[j] * kv + (r == c ? diag_add[j] : 0.0);
   } else {
     v = (r == c) ? 1.0 : 0.0;

@@ -8,17 +8,10 @@
 // mean privately (no shuffles needed: a thread owns its query row) and, when the variance is wanted, writes the four
 // K* values as one 32-byte group into the k-chunk-major, XOR-swizzled workspace the variance GEMM bulk-loads.
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace bosip {
 
-template <int KERNEL>
-__device__ __forceinline__ double kernel_value(double r2) {
-  // r2 already carries the kernel constant (scale = c/lambda with c = 1/sqrt2, sqrt3, sqrt5), SURVEY.md App. A.1
-  if (KERNEL == BOSIP_B200_KERNEL_SE) return exp(-r2);
-  double s = sqrt(r2);
-  if (KERNEL == BOSIP_B200_KERNEL_MATERN32) return (1.0 + s) * exp(-s);
-  return (1.0 + s + r2 * (1.0 / 3.0)) * exp(-s);
-}
 
 template <int KERNEL, int DP, bool WRITE_K>
 __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict__ Us, const double* __restrict__ scale,
@@ -68,7 +61,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
     }
     double kv[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) kv[e] = kernel_value<KERNEL>(r2[e]);
+    for (int e = 0; e < 4; ++e) kv[e] = kernel_from_r2<KERNEL>(r2[e]);
     const double2 a01 = *reinterpret_cast<const double2*>(sa + n);
     const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 2);
     acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);

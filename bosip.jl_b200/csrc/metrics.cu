@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace bosip {
 
@@ -14,13 +15,6 @@ namespace bosip {
 constexpr int MMD_TILE = 128;
 constexpr int MMD_STRIP = 16;  // column tiles per CTA
 
-template <int KERNEL>
-__device__ __forceinline__ double mmd_kval(double r2) {
-  if (KERNEL == BOSIP_B200_KERNEL_SE) return exp(-r2);
-  double s = sqrt(r2);
-  if (KERNEL == BOSIP_B200_KERNEL_MATERN32) return (1.0 + s) * exp(-s);
-  return (1.0 + s + r2 * (1.0 / 3.0)) * exp(-s);
-}
 
 // Ps/Qs: scaled points, SoA [dp][np] / [dp][nq] (zero padded to multiples of 128 in count; padded points are masked)
 template <int KERNEL, int DP>
@@ -60,13 +54,13 @@ mmd_kernel(const double* __restrict__ Ps, long long np, long long np_pad, const 
           r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]); r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] += mmd_kval<KERNEL>(r2[e]);
+        for (int e = 0; e < 4; ++e) acc[e] += kernel_from_r2<KERNEL>(r2[e]);
       }
       for (; jj < jmax; ++jj) {
         double r2 = 0.0;
 #pragma unroll
         for (int k = 0; k < DP; ++k) { const double t = pi[k] - sq[k][jj]; r2 = fma(t, t, r2); }
-        acc[0] += mmd_kval<KERNEL>(r2);
+        acc[0] += kernel_from_r2<KERNEL>(r2);
       }
       const double w = (symmetric && ct != rt) ? 2.0 : 1.0;
       if (row_ok) total += w * ((acc[0] + acc[1]) + (acc[2] + acc[3]));

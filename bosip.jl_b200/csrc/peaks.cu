@@ -2,6 +2,7 @@
 // TFLOP/s only; SURVEY.md section 8(d) asks for a DMMA and a DFMA figure measured on the box.
 // (tools/fp64_microbench.cu is the long form: all mma.sync f64 shapes lower to DMMA.8x8x4 on sm_100a.)
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace bosip {
 
@@ -59,6 +60,33 @@ int fp64_peak(Ctx* ctx, double* dmma, double* dfma) {
   const double warps = (double)grid * block / 32;
   if (dmma) *dmma = 2.0 * 256.0 * 8 * iters * warps / best_mma * 1e-9;
   if (dfma) *dfma = 2.0 * 8 * iters * (double)grid * block / best_fma * 1e-9;
+  return 0;
+}
+
+// self-test of fastmath.cuh against the CUDA library (host buffers)
+__global__ void math_selftest_kernel(const double* __restrict__ x, long long n, double* __restrict__ e_fast, double* __restrict__ q_fast,
+                                     double* __restrict__ e_ref, double* __restrict__ q_ref) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  e_fast[i] = fast_exp_neg(v); q_fast[i] = fast_sqrt(v);
+  e_ref[i] = exp(-v); q_ref[i] = sqrt(v);
+}
+
+int math_selftest(Ctx* ctx, const double* x, int64_t n, double* e_fast, double* q_fast, double* e_ref, double* q_ref) {
+  if (n <= 0) return 0;
+  cudaStream_t st = ctx->s_comp;
+  double* d = nullptr;
+  BOSIP_CUDA(ctx, cudaMalloc(&d, (size_t)n * 5 * 8));
+  cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, (long long)n, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
+    double* outs[4] = {e_fast, q_fast, e_ref, q_ref};
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaMemcpyAsync(outs[k], d + (size_t)(k + 1) * n, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  cudaFree(d);
+  BOSIP_CUDA(ctx, e);
   return 0;
 }
 
