@@ -671,7 +671,9 @@ class MMDMetric:
 
 
 def _lme(m: float, s: float, G: int) -> float:
-    return m if math.isinf(m) else m + math.log(s) - math.log(G)
+    if math.isinf(m) or s <= 0.0:   # empty / all -Inf, or an exactly-zero scaled sum (identical distributions)
+        return m if math.isinf(m) else -math.inf
+    return m + math.log(s) - math.log(G)
 
 
 def calc_tv(log_ws, approx_logvals, true_logvals, ctx: Optional[Context] = None) -> float:

@@ -63,7 +63,7 @@ static void t_collect(Ctx* ctx) {  // call after the stream has been synchronise
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
-static int ensure_ws(Ctx* ctx, size_t bytes) {
+int ensure_ws(Ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_bytes) return 0;
   if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
   BOSIP_CUDA(ctx, cudaMalloc(&ctx->ws, bytes));

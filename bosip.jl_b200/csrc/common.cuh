@@ -142,6 +142,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 #endif
 
 // ------------------------------------------------------------------ cross-TU host entry points
+// api.cu: grow-only device workspace of the context (valid until the next call that needs a bigger one)
+int ensure_ws(Ctx* ctx, size_t bytes);
 // kstar.cu
 int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit,
                  int nspan, double* Ks, double* mu_part, bool write_k, cudaStream_t st);

@@ -148,23 +148,22 @@ int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double*
     if (!(lambda[k] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "length-scales must be > 0");
     h_scale[k] = ck / lambda[k];
   }
-  double *dA = nullptr, *dB = nullptr, *As = nullptr, *Bs = nullptr, *dscale = nullptr, *partial = nullptr, *dout = nullptr;
-  struct Tmps { double** v[7]; ~Tmps() { for (auto q : v) if (*q) cudaFree(*q); } } tmps{{&dA, &dB, &As, &Bs, &dscale, &partial, &dout}};
   const long long max_tiles = (np > mp ? np : mp) / MMD_TILE;
   const long long max_parts = max_tiles * ((max_tiles + MMD_STRIP - 1) / MMD_STRIP);
-  BOSIP_CUDA(ctx, cudaMalloc(&As, (size_t)dp * np * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&Bs, (size_t)dp * mp * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dscale, dp * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&partial, (size_t)max_parts * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dout, 3 * 8));
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_As = carve((size_t)dp * np * 8), o_Bs = carve((size_t)dp * mp * 8), o_scale = carve((size_t)dp * 8),
+               o_part = carve((size_t)max_parts * 8), o_out = carve(3 * 8);
+  const size_t o_dA = mem == BOSIP_B200_HOST ? carve((size_t)d * n * 8) : 0, o_dB = mem == BOSIP_B200_HOST ? carve((size_t)d * m * 8) : 0;
+  BOSIP_TRY(ensure_ws(ctx, off));
+  auto D = [&](size_t o) { return reinterpret_cast<double*>(ctx->ws + o); };
+  double *As = D(o_As), *Bs = D(o_Bs), *dscale = D(o_scale), *partial = D(o_part), *dout = D(o_out);
   BOSIP_CUDA(ctx, cudaMemcpyAsync(dscale, h_scale.data(), dp * 8, cudaMemcpyHostToDevice, st));
   const double *pA = A, *pB = B;
   if (mem == BOSIP_B200_HOST) {
-    BOSIP_CUDA(ctx, cudaMalloc(&dA, (size_t)d * n * 8));
-    BOSIP_CUDA(ctx, cudaMalloc(&dB, (size_t)d * m * 8));
-    BOSIP_CUDA(ctx, cudaMemcpyAsync(dA, A, (size_t)d * n * 8, cudaMemcpyHostToDevice, st));
-    BOSIP_CUDA(ctx, cudaMemcpyAsync(dB, B, (size_t)d * m * 8, cudaMemcpyHostToDevice, st));
-    pA = dA; pB = dB;
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_dA), A, (size_t)d * n * 8, cudaMemcpyHostToDevice, st));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_dB), B, (size_t)d * m * 8, cudaMemcpyHostToDevice, st));
+    pA = D(o_dA); pB = D(o_dB);
   }
   mmd_scale_kernel<<<dim3((unsigned)((np + 255) / 256), dp), 256, 0, st>>>(pA, n, np, d, dp, dscale, As);
   mmd_scale_kernel<<<dim3((unsigned)((mp + 255) / 256), dp), 256, 0, st>>>(pB, m, mp, d, dp, dscale, Bs);
@@ -188,10 +187,20 @@ __host__ __device__ inline Lse lse_merge(Lse a, Lse b) {
   else { r.m = b.m; r.s = (b.m == INFINITY) ? b.s : b.s + a.s * exp(a.m - b.m); }
   return r;
 }
-__device__ __forceinline__ void lse_push(Lse& a, double v) {
-  if (v == -INFINITY) return;
-  if (v > a.m) { a.s = (a.m == -INFINITY) ? 1.0 : a.s * exp(a.m - v) + 1.0; a.m = v; }
-  else a.s += (v == INFINITY) ? 1.0 : exp(v - a.m);
+// Scaled-sum accumulator: value = exp(m) * s.  Batches of TV_B elements are folded with ONE rescale and TV_B independent
+// branch-free exps (fastmath.cuh), instead of a serial, branchy online update per element.
+constexpr int TV_B = 4;
+__device__ __forceinline__ void lse_push_batch(Lse& acc, const double (&v)[TV_B]) {
+  double vm = v[0];
+#pragma unroll
+  for (int e = 1; e < TV_B; ++e) vm = fmax(vm, v[e]);
+  if (vm == -INFINITY) return;                        // nothing to add
+  if (vm == INFINITY) { acc.m = INFINITY; acc.s = 1.0; return; }
+  const double nm = fmax(acc.m, vm);
+  double s = (acc.m == -INFINITY) ? 0.0 : acc.s * fast_exp_neg(nm - acc.m);
+#pragma unroll
+  for (int e = 0; e < TV_B; ++e) s += fast_exp_neg(nm - v[e]);   // v = -Inf -> exp(-Inf) = 0
+  acc.m = nm; acc.s = s;
 }
 __device__ __forceinline__ Lse lse_block(Lse x, Lse* sh) {
 #pragma unroll
@@ -216,26 +225,34 @@ __device__ __forceinline__ Lse lse_block(Lse x, Lse* sh) {
   return x;
 }
 
-// out[block] = {max_a, sum_a, max_t, sum_t}
+// out[block] = {max_a, sum_a, max_t, sum_t}: log-sum-exp pairs of lw+a and lw+t over the block's contiguous slice
 __global__ void __launch_bounds__(256)
 tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
                  double* __restrict__ out) {
   __shared__ Lse sh[8];
   Lse la{-INFINITY, 0.0}, lt{-INFINITY, 0.0};
-  // contiguous slice per block keeps the merge order independent of the launch geometry's interleaving
   const long long per = (G + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const double w = lw[i];
-    lse_push(la, w + a[i]);
-    lse_push(lt, w + t[i]);
+  for (long long i0 = lo + (long long)threadIdx.x * TV_B; i0 < hi; i0 += (long long)blockDim.x * TV_B) {
+    double va[TV_B], vt[TV_B];
+#pragma unroll
+    for (int e = 0; e < TV_B; ++e) {
+      const long long i = i0 + e;
+      const bool ok = i < hi;
+      const double w = ok ? lw[i] : 0.0;
+      va[e] = ok ? w + a[i] : -INFINITY;
+      vt[e] = ok ? w + t[i] : -INFINITY;
+    }
+    lse_push_batch(la, va);
+    lse_push_batch(lt, vt);
   }
   la = lse_block(la, sh);
   lt = lse_block(lt, sh);
   if (threadIdx.x == 0) { out[4 * blockIdx.x + 0] = la.m; out[4 * blockIdx.x + 1] = la.s; out[4 * blockIdx.x + 2] = lt.m; out[4 * blockIdx.x + 3] = lt.s; }
 }
 
-// out[block] = {max, sum} of lw + log|exp(a - eva) - exp(t - evt)|   (tv.jl:64-70)
+// out[block] = {m, s} with exp(m) * s = sum_i exp(lw_i) |exp(a_i - eva) - exp(t_i - evt)|  (tv.jl:64-70).  The log of the
+// reference's `log.(diffs)` is never taken: each term is formed directly at the running scale m >= lw + max(a~, t~).
 __global__ void __launch_bounds__(256)
 tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
                  double eva, double evt, int a_inf, int t_inf, double* __restrict__ out) {
@@ -243,10 +260,25 @@ tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, co
   Lse ld{-INFINITY, 0.0};
   const long long per = (G + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
-  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const double ea = a_inf ? 0.0 : exp(a[i] - eva);
-    const double et = t_inf ? 0.0 : exp(t[i] - evt);
-    lse_push(ld, lw[i] + log(fabs(ea - et)));
+  for (long long i0 = lo + (long long)threadIdx.x * TV_B; i0 < hi; i0 += (long long)blockDim.x * TV_B) {
+    double ua[TV_B], ut[TV_B];
+    double vm = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < TV_B; ++e) {
+      const long long i = i0 + e;
+      const bool ok = i < hi;
+      const double w = ok ? lw[i] : -INFINITY;
+      ua[e] = (ok && !a_inf) ? w + (a[i] - eva) : -INFINITY;   // log of the weighted normalised approx density
+      ut[e] = (ok && !t_inf) ? w + (t[i] - evt) : -INFINITY;
+      vm = fmax(vm, fmax(ua[e], ut[e]));
+    }
+    if (vm == -INFINITY) continue;
+    if (vm == INFINITY) { ld.m = INFINITY; ld.s = 1.0; continue; }
+    const double nm = fmax(ld.m, vm);
+    double s = (ld.m == -INFINITY) ? 0.0 : ld.s * fast_exp_neg(nm - ld.m);
+#pragma unroll
+    for (int e = 0; e < TV_B; ++e) s += fabs(fast_exp_neg(nm - ua[e]) - fast_exp_neg(nm - ut[e]));
+    ld.m = nm; ld.s = s;
   }
   ld = lse_block(ld, sh);
   if (threadIdx.x == 0) { out[2 * blockIdx.x + 0] = ld.m; out[2 * blockIdx.x + 1] = ld.s; }
@@ -256,19 +288,22 @@ static int tv_common(Ctx* ctx, const double* lw, const double* a, const double* 
                      double evt, double* out) {
   if (G < 1 || !lw || !a || !t || !out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad TV arguments");
   cudaStream_t st = ctx->s_comp;
-  double *dl = nullptr, *da = nullptr, *dt = nullptr, *dpart = nullptr;
-  struct Tmps { double** v[4]; ~Tmps() { for (auto q : v) if (*q) cudaFree(*q); } } tmps{{&dl, &da, &dt, &dpart}};
+  const int nblocks = (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 8 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 8);
+  const int width = stage == 1 ? 4 : 2;
+  const size_t part_bytes = ((size_t)nblocks * width * 8 + 255) / 256 * 256;
+  const size_t vec_bytes = ((size_t)G * 8 + 255) / 256 * 256;
+  BOSIP_TRY(ensure_ws(ctx, part_bytes + (mem == BOSIP_B200_HOST ? 3 * vec_bytes : 0)));
+  double* dpart = reinterpret_cast<double*>(ctx->ws);
   const double *pl = lw, *pa = a, *pt = t;
   if (mem == BOSIP_B200_HOST) {
-    BOSIP_CUDA(ctx, cudaMalloc(&dl, (size_t)G * 8)); BOSIP_CUDA(ctx, cudaMalloc(&da, (size_t)G * 8)); BOSIP_CUDA(ctx, cudaMalloc(&dt, (size_t)G * 8));
+    double* dl = reinterpret_cast<double*>(ctx->ws + part_bytes);
+    double* da = reinterpret_cast<double*>(ctx->ws + part_bytes + vec_bytes);
+    double* dt = reinterpret_cast<double*>(ctx->ws + part_bytes + 2 * vec_bytes);
     BOSIP_CUDA(ctx, cudaMemcpyAsync(dl, lw, (size_t)G * 8, cudaMemcpyHostToDevice, st));
     BOSIP_CUDA(ctx, cudaMemcpyAsync(da, a, (size_t)G * 8, cudaMemcpyHostToDevice, st));
     BOSIP_CUDA(ctx, cudaMemcpyAsync(dt, t, (size_t)G * 8, cudaMemcpyHostToDevice, st));
     pl = dl; pa = da; pt = dt;
   }
-  const int nblocks = (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 8 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 8);
-  const int width = stage == 1 ? 4 : 2;
-  BOSIP_CUDA(ctx, cudaMalloc(&dpart, (size_t)nblocks * width * 8));
   if (stage == 1) tv_stage1_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, dpart);
   else tv_stage2_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, eva, evt, isinf(eva) ? 1 : 0, isinf(evt) ? 1 : 0, dpart);
   BOSIP_CUDA(ctx, cudaGetLastError());
