@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 TOTAL_CANDIDATES = 10 ** 8
 PER_GPU = TOTAL_CANDIDATES // 8          # 1.25e7 candidates per GPU per step
 SEED = 20261019 + 3
-CPU_SAMPLE = 2 * 65536                    # bounded CPU-baseline sample (two 65 536-point chunks)
+CPU_SAMPLE = 65536                        # bounded CPU-baseline sample (one 65 536-point chunk, ~17 s)
 METRIC = "query pts/sec, approx_posterior+MaxVar at N=1000 d=5"
 UNIT = "points/s"
 
@@ -150,6 +150,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: libbosip_b200 has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
+    # keep NCCL's own chatter (e.g. "NCCL version ...") off stdout: the driver parses ONE JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -233,7 +237,7 @@ def main():
         vg_ms = vg["ms"] / max(1, vg["launches"])
         achieved = fl["var"] * pts_per_launch / (vg_ms * 1e-3) * 1e-12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_vargemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "vargemm_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         out = {
