@@ -61,6 +61,9 @@ PROTOTYPES = {
     "bosip_b200_posterior_eval_argmax": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
                                                    C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p,
                                                    C.c_int, C.c_int64, c_int64_p, c_double_p]),
+    "bosip_b200_posterior_eval_bi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p,
+                                               C.c_int64, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p,
+                                               C.c_int, C.c_int64, c_int64_p, c_double_p]),
     "bosip_b200_normal_likelihood_eval": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.c_void_p, C.c_void_p, C.c_int64,
                                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, c_int64_p]),

@@ -247,17 +247,23 @@ class BosipProblem:
     ctx: Optional[Context] = None
     _post: Optional["B200GPPosterior"] = field(default=None, repr=False)
 
-    def model_posterior(self) -> "B200GPPosterior":
+    def model_posterior(self):
+        """BOSS.model_posterior(problem): one posterior for MAP parameters (UniFittedParams), a list of posteriors when
+        `model` is a list of hyper-parameter samples (MultiFittedParams, src/posterior/log_posterior.jl:86-89)."""
         if self._post is None:
-            self._post = model_posterior(self.model, self.X, self.Y, ctx=self.ctx)
+            if isinstance(self.model, (list, tuple)):
+                self._post = [model_posterior(m, self.X, self.Y, ctx=self.ctx) for m in self.model]
+            else:
+                self._post = model_posterior(self.model, self.X, self.Y, ctx=self.ctx)
         return self._post
 
     def augment(self, x_new: np.ndarray, y_new: np.ndarray):
         """BOSS.augment_dataset!: append simulations; the cached posterior is dropped."""
         self.X = np.concatenate([self.X, np.asarray(x_new, float).reshape(self.X.shape[0], -1)], axis=1)
         self.Y = np.concatenate([self.Y, np.asarray(y_new, float).reshape(self.Y.shape[0], -1)], axis=1)
-        if self._post is not None:
-            self._post.free()
+        for q in (self._post if isinstance(self._post, list) else [self._post]):
+            if q is not None:
+                q.free()
         self._post = None
 
 
@@ -359,6 +365,9 @@ def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optiona
     """One fused call: returns dict of the requested length-M outputs + 'n_clamped'; with `acq` (MaxVar()/LogMaxVar()) also
     'best_idx' (index_offset + position) and 'best_val' from the same sweep.  `out` may hold preallocated output buffers
     (dict name -> array/tensor in the same memory space as X)."""
+    ensemble = list(post) if isinstance(post, (list, tuple)) else None   # MultiFittedParams: hyper-parameter samples
+    if ensemble is not None:
+        post = ensemble[0]
     vec = (np.ndim(X) == 1) if not _is_torch(X) else (X.dim() == 1)
     Xm = X.reshape(post.d, 1) if vec else X
     keep, addr, mem, M = _colmajor(Xm, post.d)
@@ -385,9 +394,15 @@ def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optiona
         else:
             ptrs.append(None)
     ncl = C.c_int64(0); bi = C.c_int64(-1); bv = C.c_double(0.0)
-    post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval_argmax(
-        post.h, C.byref(lk), C.byref(pr), addr, M, mem, maddr, want, ptrs[0], ptrs[1], ptrs[2], C.byref(ncl),
-        acq.acq_id if acq is not None else -1, index_offset, C.byref(bi), C.byref(bv)))
+    if ensemble is None:
+        post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval_argmax(
+            post.h, C.byref(lk), C.byref(pr), addr, M, mem, maddr, want, ptrs[0], ptrs[1], ptrs[2], C.byref(ncl),
+            acq.acq_id if acq is not None else -1, index_offset, C.byref(bi), C.byref(bv)))
+    else:
+        hs = (C.c_void_p * len(ensemble))(*[q.h for q in ensemble])
+        post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval_bi(
+            hs, len(ensemble), C.byref(lk), C.byref(pr), addr, M, mem, maddr, want, ptrs[0], ptrs[1], ptrs[2], C.byref(ncl),
+            acq.acq_id if acq is not None else -1, index_offset, C.byref(bi), C.byref(bv)))
     if vec:
         outs = {k: float(v[0]) for k, v in outs.items()}
     outs["n_clamped"] = ncl.value
@@ -472,20 +487,24 @@ def log_sq_likelihood_mean(like: NormalLikelihood, post):
 
 # likelihood-level closures (no prior): src/posterior/likelihood.jl:19-59.  A device-backed GP posterior takes the fused
 # path (one ccall per X); any other ModelPosterior goes through its own mean/var and the Likelihood-API kernel.
+def _device_backed(post) -> bool:
+    return isinstance(post, B200GPPosterior) or (isinstance(post, (list, tuple)) and all(isinstance(q, B200GPPosterior) for q in post))
+
+
 def log_approx_likelihood(like: NormalLikelihood, post):
-    if isinstance(post, B200GPPosterior):
+    if _device_backed(post):
         return _closure(post, like, None, L.WANT_APPROX, "log_approx_post")
     return _generic(like, post, "loglike", False)
 
 
 def log_likelihood_mean(like: NormalLikelihood, post):
-    if isinstance(post, B200GPPosterior):
+    if _device_backed(post):
         return _closure(post, like, None, L.WANT_MEAN, "log_post_mean")
     return _generic(like, post, "log_like_mean", True)
 
 
 def log_likelihood_variance(like: NormalLikelihood, post):
-    if isinstance(post, B200GPPosterior):
+    if _device_backed(post):
         return _closure(post, like, None, L.WANT_VAR, "log_post_var")
     return _generic(like, post, "log_like_var", True)
 

@@ -124,6 +124,8 @@ static int make_epi(Ctx* ctx, const Gp* gp, const bosip_b200_like_normal* like, 
 // What one evaluation sweep does.  Pointers in "user space" follow `mem`.
 struct Sweep {
   Gp* gp = nullptr;
+  std::vector<Gp*> fits;          // BI ensemble (hyper-parameter samples); empty => {gp}
+  std::vector<EpiParams> fit_ep;   // per-sample epilogue parameters (kxx, sigma^2, options differ per sample)
   EpiParams ep;
   bool use_like = false;
   int mem = BOSIP_B200_HOST;
@@ -142,7 +144,9 @@ struct Sweep {
 };
 
 static int run_sweep(Ctx* ctx, Sweep& sw) {
-  Gp* gp = sw.gp;
+  if (sw.fits.empty()) { sw.fits.push_back(sw.gp); sw.fit_ep.push_back(sw.ep); }
+  Gp* gp = sw.fits[0];
+  const int n_fits = (int)sw.fits.size();
   const int p = gp->p, d = gp->d, Ns = gp->Ns;
   const int64_t M = sw.M;
   if (M < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "M must be >= 0");
@@ -240,16 +244,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
       if (sw.logprior) lpin_dev = sw.logprior + c0;
     }
     // ---------------- compute
-    ctx->launches += 2 + (sw.need_var ? 1 : 0) + (gen ? 1 : 0) + (sw.do_argmax ? 2 : 0) + (sw.do_evidence ? 2 : 0);
-    t_begin(ctx, 0, sc);
-    BOSIP_TRY(launch_kstar(ctx, gp, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var, sc));
-    t_end(ctx, sc);
-    if (sw.need_var) {
-      t_begin(ctx, 1, sc);
-      BOSIP_TRY(launch_vargemm(ctx, gp, Ks, mc, m_tiles, q_part, sc));
-      t_end(ctx, sc);
-    }
-    (void)mcu;
+    ctx->launches += n_fits * (2 + (sw.need_var ? 1 : 0)) + (n_fits > 1 ? 1 : 0) + (gen ? 1 : 0) + (sw.do_argmax ? 2 : 0) + (sw.do_evidence ? 2 : 0);
     double* mu_o = sw.mu ? (host ? D(o_mu[b]) : sw.mu + (size_t)c0 * p) : nullptr;
     double* var_o = sw.var ? (host ? D(o_var[b]) : sw.var + (size_t)c0 * p) : nullptr;
     double* la_o = o_la[b] ? D(o_la[b]) : (sw.la ? sw.la + c0 : nullptr);
@@ -257,9 +252,23 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     double* lv_o = o_lv[b] ? D(o_lv[b]) : (sw.lv ? sw.lv + c0 : nullptr);
     double* lp_o = o_lp[b] ? D(o_lp[b]) : nullptr;
     if (!sw.use_like) { la_o = lm_o = lv_o = lp_o = nullptr; }
-    t_begin(ctx, 2, sc);
-    BOSIP_TRY(launch_epilogue(ctx, gp, sw.ep, x_dev, lpin_dev, mean_dev, mv, mc, nsplit, mu_part, sw.need_var, q_part, mu_o, var_o,
-                              lp_o, la_o, lm_o, lv_o, counters, (uint64_t)c0, sc));
+    for (int f = 0; f < n_fits; ++f) {
+      Gp* gf = sw.fits[f];
+      t_begin(ctx, 0, sc);
+      BOSIP_TRY(launch_kstar(ctx, gf, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var, sc));
+      t_end(ctx, sc);
+      if (sw.need_var) {
+        t_begin(ctx, 1, sc);
+        BOSIP_TRY(launch_vargemm(ctx, gf, Ks, mc, m_tiles, q_part, sc));
+        t_end(ctx, sc);
+      }
+      t_begin(ctx, 2, sc);
+      BOSIP_TRY(launch_epilogue(ctx, gf, sw.fit_ep[f], x_dev, lpin_dev, mean_dev, mv, mc, nsplit, mu_part, sw.need_var, q_part, mu_o, var_o,
+                                lp_o, la_o, lm_o, lv_o, counters, (uint64_t)c0, n_fits == 1 ? 0 : (f == 0 ? 1 : 2), sc));
+      if (f + 1 < n_fits) t_end(ctx, sc);
+    }
+    if (n_fits > 1) BOSIP_TRY(launch_bi_finish(ctx, sw.ep, x_dev, lpin_dev, mv, n_fits, lp_o, la_o, lm_o, lv_o, sc));
+    (void)mcu;
     if (sw.do_argmax)
       BOSIP_TRY(launch_argmax_chunk(ctx, lv_o, mv, sw.index_offset + c0, sw.exp_vals, D(o_scr_v), reinterpret_cast<long long*>(D(o_scr_i)),
                                     scal + 0, reinterpret_cast<long long*>(scal + 1), sc));
@@ -471,6 +480,46 @@ int bosip_b200_posterior_eval_argmax(bosip_b200_gp* gh, const bosip_b200_like_no
   sw.need_var = do_arg || (want & (BOSIP_B200_WANT_MEAN | BOSIP_B200_WANT_VAR)) != 0;
   sw.do_argmax = do_arg; sw.exp_vals = (acq == BOSIP_B200_ACQ_MAXVAR) ? 1 : 0; sw.index_offset = index_offset;
   BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
+  if (prior && prior->logprior) sw.logprior = prior->logprior;
+  int rc = run_sweep(ctx, sw);
+  if (n_clamped) *n_clamped = sw.n_clamped;
+  if (do_arg) { *best_idx = sw.best_idx; *best_val = sw.best_idx >= 0 ? sw.best_val : -INFINITY; }
+  return rc;
+}
+
+int bosip_b200_posterior_eval_bi(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like,
+                                 const bosip_b200_prior* prior, const double* Xq, int64_t M, int mem, const double* mean_at_Xq,
+                                 unsigned want, double* log_approx_post, double* log_post_mean, double* log_post_var,
+                                 int64_t* n_clamped, int acq, int64_t index_offset, int64_t* best_idx, double* best_val) {
+  if (!gps || n_samples < 1 || !gps[0] || !gps[0]->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gps[0]->g->ctx);
+  API_LOCK(h);
+  if (!like) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood is NULL");
+  if (!Xq && M > 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "Xq is NULL");
+  const bool do_arg = acq >= 0;
+  if (do_arg && acq != BOSIP_B200_ACQ_MAXVAR && acq != BOSIP_B200_ACQ_LOGMAXVAR) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown acquisition");
+  if (do_arg && (!best_idx || !best_val || index_offset < 0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "argmax outputs are required");
+  if ((want & 7u) == 0 && !do_arg) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "`want` selects no output");
+  if (((want & BOSIP_B200_WANT_APPROX) && !log_approx_post) || ((want & BOSIP_B200_WANT_MEAN) && !log_post_mean) ||
+      ((want & BOSIP_B200_WANT_VAR) && !log_post_var))
+    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "an output selected by `want` is NULL");
+  Sweep sw;
+  sw.gp = gps[0]->g; sw.mem = mem; sw.xq = Xq; sw.M = M; sw.mean_at_xq = mean_at_Xq; sw.use_like = true;
+  sw.la = (want & BOSIP_B200_WANT_APPROX) ? log_approx_post : nullptr;
+  sw.lm = (want & BOSIP_B200_WANT_MEAN) ? log_post_mean : nullptr;
+  sw.lv = (want & BOSIP_B200_WANT_VAR) ? log_post_var : nullptr;
+  sw.need_var = do_arg || (want & (BOSIP_B200_WANT_MEAN | BOSIP_B200_WANT_VAR)) != 0;
+  sw.do_argmax = do_arg; sw.exp_vals = (acq == BOSIP_B200_ACQ_MAXVAR) ? 1 : 0; sw.index_offset = index_offset;
+  for (int f = 0; f < n_samples; ++f) {
+    if (!gps[f] || !gps[f]->g) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "NULL GP handle in the ensemble");
+    Gp* g = gps[f]->g;
+    if (g->ctx != sw.gp->ctx || g->d != sw.gp->d || g->p != sw.gp->p || g->N != sw.gp->N || g->kernel_id != sw.gp->kernel_id)
+      BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "all hyper-parameter samples must share context, kernel, d, p and N");
+    EpiParams e;
+    BOSIP_TRY(make_epi(ctx, g, like, prior, &e));
+    sw.fits.push_back(g); sw.fit_ep.push_back(e);
+  }
+  sw.ep = sw.fit_ep[0];  // carries the prior for bi_finish
   if (prior && prior->logprior) sw.logprior = prior->logprior;
   int rc = run_sweep(ctx, sw);
   if (n_clamped) *n_clamped = sw.n_clamped;

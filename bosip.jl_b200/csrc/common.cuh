@@ -154,7 +154,9 @@ int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* x
                     const double* mean_at_xq, int64_t m_valid, int64_t mc, int nsplit, const double* mu_part,
                     bool have_var, const double* q_part, double* mu_out, double* var_out, double* lp_out,
                     double* log_approx, double* log_mean, double* log_var, unsigned long long* counters,
-                    uint64_t index_base, cudaStream_t st);
+                    uint64_t index_base, int bi_mode, cudaStream_t st);
+int launch_bi_finish(Ctx* ctx, const EpiParams& ep, const double* xq, const double* logprior, int64_t m_valid, int n_samples,
+                     double* lp_out, double* la, double* lm, double* lv, cudaStream_t st);
 int launch_argmax_chunk(Ctx* ctx, const double* vals, int64_t m_valid, int64_t global_offset, int exp_vals,
                         double* scratch_val, long long* scratch_idx, double* best_val, long long* best_idx,
                         cudaStream_t st);

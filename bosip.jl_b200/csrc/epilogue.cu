@@ -49,14 +49,19 @@ epilogue_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__
                 const double* __restrict__ mu_part, int have_var, const double* __restrict__ q_part,
                 double* __restrict__ mu_out, double* __restrict__ var_out, double* __restrict__ lp_out,
                 double* __restrict__ log_approx, double* __restrict__ log_mean, double* __restrict__ log_var,
-                unsigned long long* __restrict__ counters, unsigned long long index_base) {
+                unsigned long long* __restrict__ counters, unsigned long long index_base, int bi_mode) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= m_valid) return;
   const int p = ep.p;
 
+  // bi_mode 0: one fit, outputs are the log-closures.  bi_mode 1/2: hyper-parameter sample s of a BI ensemble
+  // (src/posterior/log_posterior.jl:86-95,120-129,153-162): the outputs ACCUMULATE exp(log-likelihood term) in linear space
+  // (1: first sample, store; 2: add); the prior and the log are applied once by bi_finish_kernel.
   double lp = 0.0;
-  if (ep.has_prior == 2) lp = logprior[m];
-  else if (ep.has_prior == 1) lp = log_prior_point(ep, xq + m * ep.d);
+  if (bi_mode == 0) {
+    if (ep.has_prior == 2) lp = logprior[m];
+    else if (ep.has_prior == 1) lp = log_prior_point(ep, xq + m * ep.d);
+  }
 
   double plug = 0.0, lm = 0.0, lsq = 0.0;
   for (int j = 0; j < p; ++j) {
@@ -78,10 +83,10 @@ epilogue_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__
       lsq += normlogpdf(mu, sqrt((so2 + 2.0 * var) / 2.0), z);
     }
   }
-  if (lp_out) lp_out[m] = lp;
-  if (log_approx) log_approx[m] = lp + plug;
+  if (bi_mode == 0 && lp_out) lp_out[m] = lp;
+  if (log_approx) log_approx[m] = bi_mode == 0 ? lp + plug : (bi_mode == 1 ? exp(plug) : log_approx[m] + exp(plug));
   if (have_var) {
-    if (log_mean) log_mean[m] = lp + lm;
+    if (log_mean) log_mean[m] = bi_mode == 0 ? lp + lm : (bi_mode == 1 ? exp(lm) : log_mean[m] + exp(lm));
     if (log_var) {
       const double log_sq = ep.log_C + lsq;
       double v = exp(log_sq) - exp(2.0 * lm);
@@ -93,22 +98,46 @@ epilogue_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__
           atomicMin(&counters[1], index_base + (unsigned long long)m);
         }
       }
-      log_var[m] = 2.0 * lp + log(v);
+      log_var[m] = bi_mode == 0 ? 2.0 * lp + log(v) : (bi_mode == 1 ? v : log_var[m] + v);
     }
   }
+}
+
+// BI ensemble: out = k * log_prior + log(acc / S)   -- log.(mapreduce(f -> exp.(f(x)), .+, fs) ./ sample_count)
+__global__ void __launch_bounds__(256)
+bi_finish_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__ xq, const double* __restrict__ logprior,
+                 long long m_valid, double inv_s, double* __restrict__ lp_out, double* __restrict__ la, double* __restrict__ lm,
+                 double* __restrict__ lv) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= m_valid) return;
+  double lp = 0.0;
+  if (ep.has_prior == 2) lp = logprior[m];
+  else if (ep.has_prior == 1) lp = log_prior_point(ep, xq + m * ep.d);
+  if (lp_out) lp_out[m] = lp;
+  if (la) la[m] = lp + log(la[m] * inv_s);
+  if (lm) lm[m] = lp + log(lm[m] * inv_s);
+  if (lv) lv[m] = 2.0 * lp + log(lv[m] * inv_s);
+}
+
+int launch_bi_finish(Ctx* ctx, const EpiParams& ep, const double* xq, const double* logprior, int64_t m_valid, int n_samples,
+                     double* lp_out, double* la, double* lm, double* lv, cudaStream_t st) {
+  if (m_valid <= 0) return 0;
+  bi_finish_kernel<<<(unsigned)((m_valid + 255) / 256), 256, 0, st>>>(ep, xq, logprior, (long long)m_valid, 1.0 / n_samples, lp_out, la, lm, lv);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
 }
 
 int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* xq, const double* logprior,
                     const double* mean_at_xq, int64_t m_valid, int64_t mc, int nsplit, const double* mu_part,
                     bool have_var, const double* q_part, double* mu_out, double* var_out, double* lp_out,
                     double* log_approx, double* log_mean, double* log_var, unsigned long long* counters,
-                    uint64_t index_base, cudaStream_t st) {
+                    uint64_t index_base, int bi_mode, cudaStream_t st) {
   if (m_valid <= 0) return 0;
   const int block = 256;
   const unsigned grid = (unsigned)((m_valid + block - 1) / block);
   epilogue_kernel<<<grid, block, 0, st>>>(ep, xq, logprior, mean_at_xq, (long long)m_valid, (long long)mc, nsplit, 1 /* the GEMM writes one q per row */,
                                           mu_part, have_var ? 1 : 0, q_part, mu_out, var_out, lp_out, log_approx,
-                                          log_mean, log_var, counters, (unsigned long long)index_base);
+                                          log_mean, log_var, counters, (unsigned long long)index_base, bi_mode);
   BOSIP_CUDA(ctx, cudaGetLastError());
   return 0;
 }

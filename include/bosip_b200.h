@@ -162,6 +162,15 @@ int bosip_b200_posterior_eval_argmax(bosip_b200_gp* gp, const bosip_b200_like_no
                                      int64_t* n_clamped, int acq, int64_t index_offset, int64_t* best_idx,
                                      double* best_val);
 
+/* Bayesian-inference variant (MultiFittedParams, src/posterior/log_posterior.jl:86-95,120-129,153-162): an ensemble of
+ * n_samples conditioned GPs (hyper-parameter samples of the same data).  Each requested closure is
+ * k*log_prior + log( (1/S) sum_s exp(loglike-term_s(x)) ), the average taken in linear space exactly as the reference's
+ * `log.(mapreduce(f -> exp.(f(x)), .+, fs) ./ sample_count)` does.  Same outputs/argmax semantics as above. */
+int bosip_b200_posterior_eval_bi(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like,
+                                 const bosip_b200_prior* prior, const double* Xq, int64_t M, int mem, const double* mean_at_Xq,
+                                 unsigned want, double* log_approx_post, double* log_post_mean, double* log_post_var,
+                                 int64_t* n_clamped, int acq, int64_t index_offset, int64_t* best_idx, double* best_val);
+
 /* ---- the Likelihood API on its own, for ANY ModelPosterior's outputs: NormalLikelihood given mu, var (p x M each;
  *      var == NULL means zero variance).  Replaces loglike_marginal / loglike (src/likelihoods/normal.jl:28-30,
  *      src/types/likelihood.jl:53-71), log_marginal_likelihood_mean (normal.jl:32-53), log_likelihood_mean

@@ -288,6 +288,24 @@ def posterior_eval(fit: GPFit, like: NormalLikelihood, prior: ProductPrior, Xq, 
     }
 
 
+def posterior_eval_bi(fits: Sequence[GPFit], like: NormalLikelihood, prior: ProductPrior, Xq):
+    """Bayesian-inference (MultiFittedParams) closures, src/posterior/log_posterior.jl:86-95,120-129,153-162:
+    log.(mapreduce(f -> exp.(f(x)), .+, fs) ./ sample_count) over the per-sample likelihood closures (linear-space average,
+    as the reference does), then the prior added as in :19,:39,:59."""
+    lp = log_prior(prior, Xq)
+    acc = {"a": 0.0, "m": 0.0, "v": 0.0}
+    for fit in fits:
+        mu, var = gp_predict(fit, Xq)
+        std = np.sqrt(var)
+        acc["a"] = acc["a"] + np.exp(loglike(like, mu))
+        acc["m"] = acc["m"] + np.exp(log_likelihood_mean(like, mu, std))
+        acc["v"] = acc["v"] + np.exp(log_likelihood_variance(like, mu, std))
+    S = len(fits)
+    with np.errstate(divide="ignore"):
+        return {"log_prior": lp, "log_approx_post": lp + np.log(acc["a"] / S), "log_post_mean": lp + np.log(acc["m"] / S),
+                "log_post_var": 2.0 * lp + np.log(acc["v"] / S)}
+
+
 def maxvar_argmax(log_post_var: np.ndarray, log_space: bool):
     """MaxVar (src/acquisitions/maxvar.jl:9-11 -> posterior.jl:141: exp.(log V)) or LogMaxVar
     (src/acquisitions/logmaxvar.jl:13-15) evaluated on a candidate set, then Julia `argmax` semantics of BOSS's

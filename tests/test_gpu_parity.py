@@ -295,3 +295,44 @@ def test_fast_math_accuracy(bb, ctx):
     ok = x >= 1e-280
     assert np.max(np.abs(qf[ok] - qr[ok]) / qr[ok]) < 2.3e-16
     assert qf[0] == 0.0 and np.all(qf[~ok] < 1e-140)
+
+
+def test_bi_hyperparameter_samples(bb, ctx):
+    """MultiFittedParams (BI): log-mean-exp over S hyper-parameter samples in ONE fused call (a15 of SURVEY.md section 8a)."""
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, "C2")
+    rng = np.random.default_rng(21)
+    S = 5
+    models, ofits = [], []
+    for s_ in range(S):
+        lam = pr.lam * rng.uniform(0.7, 1.4, pr.lam.shape); alpha = pr.alpha * rng.uniform(0.8, 1.2, pr.p); sigma = pr.sigma * rng.uniform(0.5, 2.0, pr.p)
+        models.append(bb.GaussianProcess(pr.kernel_id, lam, alpha, sigma))
+        ofits.append(orc.gp_fit(pr.kernel_id, pr.X, pr.Y, lam, alpha, sigma))
+    Xq = queries(pr, 5000, seed=5, spill=0.05)
+    prob = bb.BosipProblem(pr.X, pr.Y, models, like, prior, (pr.lb, pr.ub), ctx)
+    posts = prob.model_posterior()
+    assert isinstance(posts, list) and len(posts) == S
+    res = bb.posterior_eval(posts, like, prior, Xq, 7, acq=bb.LogMaxVar())
+    ores = orc.posterior_eval_bi(ofits, olike, oprior, Xq)
+    for k in ("log_approx_post", "log_post_mean"):
+        fin = np.isfinite(ores[k])
+        np.testing.assert_array_equal(np.isfinite(res[k]), fin)
+        np.testing.assert_allclose(res[k][fin], ores[k][fin], rtol=TOL)
+    fin = np.isfinite(ores["log_post_var"]) & np.isfinite(res["log_post_var"])
+    assert fin.sum() > 0.5 * fin.size
+    assert np.all(np.abs(res["log_post_var"][fin] - ores["log_post_var"][fin]) <= TOL * np.abs(ores["log_post_var"][fin]) + 1e-7)
+    oi, ov = orc.maxvar_argmax(ores["log_post_var"], True)
+    assert res["best_idx"] == oi
+    # the closures of the problem object take the ensemble path, and a one-member ensemble equals the MAP path
+    np.testing.assert_array_equal(bb.log_posterior_variance(prob)(Xq), res["log_post_var"])
+    one = bb.posterior_eval([posts[0]], like, prior, Xq, 7)
+    ref = bb.posterior_eval(posts[0], like, prior, Xq, 7)
+    for k in ("log_approx_post", "log_post_mean", "log_post_var"):
+        np.testing.assert_allclose(one[k], ref[k], rtol=1e-13)
+    # chunking stays invisible
+    try:
+        ctx.set_chunk(512)
+        r2 = bb.posterior_eval(posts, like, prior, Xq, 7)
+        for k in ("log_approx_post", "log_post_mean", "log_post_var"):
+            np.testing.assert_array_equal(r2[k], res[k])
+    finally:
+        ctx.set_chunk(0)
