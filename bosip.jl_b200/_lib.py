@@ -69,6 +69,8 @@ PROTOTYPES = {
                                                     C.c_void_p, c_int64_p]),
     "bosip_b200_acq_argmax": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.POINTER(CandSrc), C.c_int64,
                                         C.c_int64, C.c_int, c_int64_p, c_double_p, c_double_p]),
+    "bosip_b200_marginals_int": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), c_double_p, C.c_int64, C.c_int,
+                                           c_double_p, c_double_p, C.c_uint, c_double_p, c_double_p]),
     "bosip_b200_candidates": (C.c_int, [C.c_void_p, C.POINTER(CandSrc), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "bosip_b200_evidence_sum": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
                                           C.c_int, C.c_uint, c_double_p]),

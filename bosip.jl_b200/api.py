@@ -735,3 +735,70 @@ def calculate_metric(metric, a, b, ctx: Optional[Context] = None) -> float:
         approx_logvals = np.asarray(b(metric.grid), float)
         return calc_tv(metric.log_ws, approx_logvals, true_logvals, ctx)
     raise TypeError(type(metric))
+
+
+# ----------------------------------------------------------------------------------------------- marginal-integration sweep
+def generate_LHC(bounds, count: int, rng: Optional[np.random.Generator] = None) -> np.ndarray:
+    """BOSS.generate_LHC(bounds, count): d x count Latin-hypercube samples (ext/CairoExt.jl:92)."""
+    rng = rng or np.random.default_rng()
+    lb, ub = np.asarray(bounds[0], float), np.asarray(bounds[1], float)
+    d = len(lb)
+    u = (np.stack([rng.permutation(count) for _ in range(d)]) + rng.uniform(size=(d, count))) / count
+    return lb[:, None] + (ub - lb)[:, None] * u
+
+
+def normalize_prob_vals(ys: np.ndarray, *steps: float) -> np.ndarray:
+    """normalize_prob_vals! (ext/CairoExt.jl:410-430): trapezoid-rule normalisation on the plotting grid."""
+    ys = np.array(ys, dtype=float)
+    if ys.ndim == 1:
+        total = ys.sum() - 0.5 * (ys[0] + ys[-1])
+        return np.full_like(ys, 1.0 / (steps[0] * (len(ys) - 1))) if total == 0.0 else ys / (steps[0] * total)
+    total = ys.sum() - 0.5 * (ys[0, :].sum() + ys[-1, :].sum() + ys[:, 0].sum() + ys[:, -1].sum())
+    total += 0.25 * (ys[0, 0] + ys[0, -1] + ys[-1, 0] + ys[-1, -1])
+    if total == 0.0:
+        return np.full_like(ys, 1.0 / (steps[0] * steps[1] * (ys.shape[0] - 1) * (ys.shape[1] - 1)))
+    return ys / (steps[0] * steps[1] * total)
+
+
+_FUNC_BITS = {"approx_posterior": L.WANT_APPROX, "posterior_mean": L.WANT_MEAN, "posterior_variance": L.WANT_VAR}
+
+
+def compute_marginals_int(bosip: BosipProblem, func: str = "posterior_mean", grid_size: int = 200, lhc_grid_size: int = 200,
+                          xs=None, plot_diagonal: bool = True, plot_pair_marginals: bool = True, rng=None, normalize: bool = True):
+    """compute_marginals_int / _compute_marginals_int (ext/CairoExt.jl:137-246) with the whole sweep on the device: the
+    (d*gs + C(d,2)*gs^2) * G query points are generated, evaluated and averaged there; only the means come back.
+    Returns {'marginals': {(a, b): {'xs': (...), 'ys': ...}}, 'bounds', 'X', 'lhc'} with 0-based dims (PlotData)."""
+    post = bosip.model_posterior()
+    if not isinstance(post, B200GPPosterior):
+        raise NotImplementedError("the device sweep needs a single conditioned GP (MAP parameters)")
+    lb, ub = (np.ascontiguousarray(b, dtype=np.float64) for b in bosip.bounds)
+    d = post.d
+    if xs is None:
+        xs = generate_LHC((lb, ub), lhc_grid_size, rng)
+    xs = np.asfortranarray(np.asarray(xs, dtype=np.float64))
+    G = xs.shape[1]
+    gs = int(grid_size)
+    npairs = d * (d - 1) // 2
+    diag = np.empty((gs, d), order="F") if plot_diagonal else None
+    pairs = np.empty((gs, gs, npairs), order="F") if (plot_pair_marginals and npairs) else None
+    lk = bosip.likelihood._c(); pr = bosip.x_prior._c()
+    post.ctx._check(post.ctx.lib.bosip_b200_marginals_int(post.h, C.byref(lk), C.byref(pr), _dptr(xs), G, gs, _dptr(lb), _dptr(ub),
+                                                         _FUNC_BITS[func], _dptr(diag) if diag is not None else None,
+                                                         _dptr(pairs) if pairs is not None else None))
+    steps = (ub - lb) / (gs - 1)                                       # plot_steps, ext/CairoExt.jl:432-435
+    axes = [np.linspace(lb[k], ub[k], gs) for k in range(d)]
+    marg = {}
+    if diag is not None:
+        for k in range(d):
+            ys = diag[:, k]
+            marg[(k, k)] = {"xs": (axes[k],), "ys": normalize_prob_vals(ys, steps[k]) if normalize else ys.copy()}
+    if pairs is not None:
+        pi = 0
+        for a in range(d):
+            for b in range(a + 1, d):
+                ys = pairs[:, :, pi]
+                ys = normalize_prob_vals(ys, steps[a], steps[b]) if normalize else ys.copy()
+                marg[(a, b)] = {"xs": (axes[a], axes[b]), "ys": ys}
+                marg[(b, a)] = {"xs": (axes[b], axes[a]), "ys": ys.T}
+                pi += 1
+    return {"marginals": marg, "bounds": (lb, ub), "X": bosip.X, "lhc": xs}

@@ -138,6 +138,7 @@ struct Sweep {
   double *mu = nullptr, *var = nullptr, *la = nullptr, *lm = nullptr, *lv = nullptr;  // user-space outputs
   bool do_argmax = false; int exp_vals = 0;
   bool do_evidence = false; unsigned evid_which = 0;
+  int64_t seg_len = 0; double* seg_out = nullptr; unsigned seg_which = 0;  // segmented mean of exp(closure): seg_out (device) [M / seg_len]
   // results
   int64_t n_clamped = 0; int64_t domain_idx = -1;
   double best_val = 0.0; int64_t best_idx = -1; double evid_sum = 0.0;
@@ -172,7 +173,9 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   }
   if (ctx->user_chunk > 0) mc = std::min(mc, round_up(ctx->user_chunk, TILE_M));
   mc = std::min(mc, round_up(M, TILE_M));
-  const int64_t nchunks = (M + mc - 1) / mc;
+  if (sw.seg_len > mc) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "segment length exceeds the chunk size");
+  const int64_t ppc = sw.seg_len > 0 ? (mc / sw.seg_len) * sw.seg_len : mc;  // points per chunk: whole segments only
+  const int64_t nchunks = (M + ppc - 1) / ppc;
 
   // ---- workspace carve-up (all sizes in doubles, 256-byte aligned pieces)
   size_t off = 0;
@@ -191,9 +194,9 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     if (host && sw.logprior) o_lpin[b] = carve((size_t)mc);
     if (host && sw.mu) o_mu[b] = carve((size_t)p * mc);
     if (host && sw.var) o_var[b] = carve((size_t)p * mc);
-    if ((host && sw.la) || (want_post_dev && sw.evid_which == BOSIP_B200_WANT_APPROX)) o_la[b] = carve((size_t)mc);
-    if ((host && sw.lm) || (want_post_dev && sw.evid_which == BOSIP_B200_WANT_MEAN)) o_lm[b] = carve((size_t)mc);
-    if ((host && sw.lv) || (sw.do_argmax && !sw.lv)) o_lv[b] = carve((size_t)mc);
+    if ((host && sw.la) || (want_post_dev && sw.evid_which == BOSIP_B200_WANT_APPROX) || (sw.seg_len > 0 && sw.seg_which == BOSIP_B200_WANT_APPROX)) o_la[b] = carve((size_t)mc);
+    if ((host && sw.lm) || (want_post_dev && sw.evid_which == BOSIP_B200_WANT_MEAN) || (sw.seg_len > 0 && sw.seg_which == BOSIP_B200_WANT_MEAN)) o_lm[b] = carve((size_t)mc);
+    if ((host && sw.lv) || (sw.do_argmax && !sw.lv) || (sw.seg_len > 0 && sw.seg_which == BOSIP_B200_WANT_VAR)) o_lv[b] = carve((size_t)mc);
     if (want_post_dev) o_lp[b] = carve((size_t)mc);
   }
   const size_t o_scr_v = carve(1024), o_scr_i = carve(1024), o_scr_s = carve(256), o_scalars = carve(8);
@@ -219,7 +222,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
 
   for (int64_t c = 0; c < nchunks; ++c) {
     const int b = (int)(c & 1);
-    const int64_t c0 = c * mc, mv = std::min(mc, M - c0);
+    const int64_t c0 = c * ppc, mv = std::min(ppc, M - c0);
     const int64_t m_tiles = (mv + TILE_M - 1) / TILE_M, mcu = m_tiles * TILE_M;  // rows actually computed this chunk
     const double *x_dev, *mean_dev = nullptr, *lpin_dev = nullptr;
     // ---------------- inputs
@@ -272,6 +275,11 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     if (sw.do_argmax)
       BOSIP_TRY(launch_argmax_chunk(ctx, lv_o, mv, sw.index_offset + c0, sw.exp_vals, D(o_scr_v), reinterpret_cast<long long*>(D(o_scr_i)),
                                     scal + 0, reinterpret_cast<long long*>(scal + 1), sc));
+    if (sw.seg_len > 0) {
+      const double* v = sw.seg_which == BOSIP_B200_WANT_APPROX ? la_o : sw.seg_which == BOSIP_B200_WANT_MEAN ? lm_o : lv_o;
+      BOSIP_TRY(launch_segmean_exp(ctx, v, mv / sw.seg_len, sw.seg_len, sw.seg_out + c0 / sw.seg_len, sc));
+      ctx->launches += 1;
+    }
     if (sw.do_evidence)
       BOSIP_TRY(launch_sum_chunk(ctx, sw.evid_which == BOSIP_B200_WANT_APPROX ? la_o : lm_o, lp_o, mv, D(o_scr_s), scal + 2, sc));
     t_end(ctx, sc);
@@ -636,6 +644,39 @@ int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like,
       BOSIP_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
     }
   }
+  return 0;
+}
+
+int bosip_b200_marginals_int(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior, const double* lhc,
+                             int64_t G, int grid_size, const double* lb, const double* ub, unsigned which, double* diag, double* pairs) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+  API_LOCK(h);
+  Gp* gp = gh->g;
+  const int d = gp->d;
+  if (!like || !lhc || !lb || !ub || G < 1 || grid_size < 2) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad arguments");
+  if (which != BOSIP_B200_WANT_APPROX && which != BOSIP_B200_WANT_MEAN && which != BOSIP_B200_WANT_VAR) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "which must be one WANT_* bit");
+  if (!diag && !pairs) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "no output requested");
+  if (prior && prior->logprior) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "the sweep generates its points on the device: a prior descriptor is required");
+  const int64_t gs = grid_size, n_diag = diag ? (int64_t)d * gs : 0, n_pairs = pairs ? (int64_t)d * (d - 1) / 2 * gs * gs : 0;
+  const int64_t n_slots = n_diag + n_pairs;
+  if (n_slots == 0) return 0;
+  double *d_lhc = nullptr, *d_out = nullptr;
+  struct Tmps { double** v[2]; ~Tmps() { for (auto q : v) if (*q) cudaFree(*q); } } tmps{{&d_lhc, &d_out}};
+  BOSIP_CUDA(ctx, cudaMalloc(&d_lhc, (size_t)d * G * 8));
+  BOSIP_CUDA(ctx, cudaMalloc(&d_out, (size_t)n_slots * 8));
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(d_lhc, lhc, (size_t)d * G * 8, cudaMemcpyHostToDevice, ctx->s_comp));
+  bosip_b200_cand_src src;
+  memset(&src, 0, sizeof(src));
+  src.kind = 3; src.points = d_lhc; src.seed = (uint64_t)G; src.mem = (int32_t)n_diag; src.lb = lb; src.ub = ub; src.n_per_dim = gs;
+  Sweep sw;
+  sw.gp = gp; sw.mem = BOSIP_B200_DEVICE; sw.xq = nullptr; sw.src = &src; sw.M = n_slots * G; sw.index_offset = 0; sw.use_like = true;
+  sw.need_var = which != BOSIP_B200_WANT_APPROX;
+  sw.seg_len = G; sw.seg_out = d_out; sw.seg_which = which;
+  BOSIP_TRY(make_epi(ctx, gp, like, prior, &sw.ep));
+  BOSIP_TRY(run_sweep(ctx, sw));
+  if (diag) BOSIP_CUDA(ctx, cudaMemcpy(diag, d_out, (size_t)n_diag * 8, cudaMemcpyDeviceToHost));
+  if (pairs) BOSIP_CUDA(ctx, cudaMemcpy(pairs, d_out + n_diag, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 

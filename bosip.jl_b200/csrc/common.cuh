@@ -165,6 +165,7 @@ int launch_sum_chunk(Ctx* ctx, const double* log_post, const double* log_prior, 
 int launch_like_eval(Ctx* ctx, const EpiParams& ep, const double* mu, const double* var, int64_t m, double* marg_approx,
                      double* l_approx, double* marg_mean, double* l_mean, double* l_sq, double* l_var,
                      unsigned long long* counters, cudaStream_t st);
+int launch_segmean_exp(Ctx* ctx, const double* v, int64_t n_seg, int64_t seg_len, double* out, cudaStream_t st);
 int launch_candidates(Ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t m, int64_t offset, double* out,
                       cudaStream_t st);
 // fit.cu

@@ -296,7 +296,18 @@ struct CandParams {
   unsigned long long seed;
   long long n_per_dim;
   double lb[MAX_D], ub[MAX_D];
+  // kind 3 (marginal-integration sweep, ext/CairoExt.jl:146-246): LHC samples d x G on the device, grid_size values per axis
+  const double* lhc;
+  long long G;
+  int n_diag_slots;  // d * grid_size when the diagonal marginals are requested, else 0
 };
+
+__device__ __forceinline__ double axis_value(const CandParams& cp, int k, long long i) {
+  const long long n = cp.n_per_dim;
+  if (n == 1) return cp.lb[k];
+  if (i == n - 1) return cp.ub[k];
+  return __dadd_rn(__dmul_rn((double)i, __ddiv_rn(__dsub_rn(cp.ub[k], cp.lb[k]), (double)(n - 1))), cp.lb[k]);
+}
 
 __global__ void __launch_bounds__(256)
 candidates_kernel(const __grid_constant__ CandParams cp, long long m, long long offset, double* __restrict__ out) {
@@ -307,6 +318,27 @@ candidates_kernel(const __grid_constant__ CandParams cp, long long m, long long 
     for (int k = 0; k < cp.d; ++k) {
       const double u = philox_unit(cp.seed, gi, k);
       out[i * cp.d + k] = __dadd_rn(cp.lb[k], __dmul_rn(__dsub_rn(cp.ub[k], cp.lb[k]), u));
+    }
+  } else if (cp.kind == 3) {
+    // slot = gi / G: diagonal slots first (dim * gs + i), then pair slots (pair (a<b) in the reference's order, ia fastest);
+    // the point is LHC sample gi % G with row dim (or rows a, b) overwritten by the slot's grid value(s)
+    const long long slot = (long long)(gi / (unsigned long long)cp.G), g = (long long)(gi % (unsigned long long)cp.G);
+    const long long gs = cp.n_per_dim;
+    int da = -1, db = -1; long long ia = 0, ib = 0;
+    if (slot < cp.n_diag_slots) { da = (int)(slot / gs); ia = slot % gs; }
+    else {
+      long long r = slot - cp.n_diag_slots;
+      long long pi = r / (gs * gs); r -= pi * gs * gs;
+      ia = r % gs; ib = r / gs;
+      int a = 0;
+      while (pi >= cp.d - 1 - a) { pi -= cp.d - 1 - a; ++a; }
+      da = a; db = a + 1 + (int)pi;
+    }
+    for (int k = 0; k < cp.d; ++k) {
+      double x = cp.lhc[(size_t)g * cp.d + k];
+      if (k == da) x = axis_value(cp, k, ia);
+      if (k == db) x = axis_value(cp, k, ib);
+      out[i * cp.d + k] = x;
     }
   } else {  // tensor grid, first coordinate fastest; matches numpy.linspace(lb, ub, n) per axis
     unsigned long long r = gi;
@@ -323,6 +355,30 @@ candidates_kernel(const __grid_constant__ CandParams cp, long long m, long long 
   }
 }
 
+// mean over each segment of `seg_len` consecutive points of exp(log-values): out[seg] = (1/seg_len) sum_g exp(v[seg*seg_len + g])
+// (the `mean(f(grid))` of ext/CairoExt.jl:184,221).  One block per segment, fixed summation order.
+__global__ void __launch_bounds__(128)
+segmean_exp_kernel(const double* __restrict__ v, long long seg_len, double* __restrict__ out) {
+  __shared__ double sh[128];
+  const double* seg = v + (size_t)blockIdx.x * seg_len;
+  double s = 0.0;
+  for (long long g = threadIdx.x; g < seg_len; g += blockDim.x) s += exp(seg[g]);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0] / (double)seg_len;
+}
+
+int launch_segmean_exp(Ctx* ctx, const double* v, int64_t n_seg, int64_t seg_len, double* out, cudaStream_t st) {
+  if (n_seg <= 0) return 0;
+  segmean_exp_kernel<<<(unsigned)n_seg, 128, 0, st>>>(v, (long long)seg_len, out);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 int launch_candidates(Ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t m, int64_t offset, double* out,
                       cudaStream_t st) {
   if (m <= 0) return 0;
@@ -330,6 +386,7 @@ int launch_candidates(Ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t m
   if (!src->lb || !src->ub) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "candidate source needs lb and ub");
   CandParams cp;
   cp.kind = src->kind; cp.d = d; cp.seed = src->seed; cp.n_per_dim = src->n_per_dim;
+  cp.lhc = src->points; cp.G = (long long)src->seed; cp.n_diag_slots = src->mem;  // kind 3 reuses these fields (internal source only)
   for (int k = 0; k < d; ++k) { cp.lb[k] = src->lb[k]; cp.ub[k] = src->ub[k]; }
   candidates_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(cp, (long long)m, (long long)offset, out);
   BOSIP_CUDA(ctx, cudaGetLastError());

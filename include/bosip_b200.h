@@ -192,6 +192,16 @@ int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* ctx, const bosip_b200_like
 int bosip_b200_acq_argmax(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
                           const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq,
                           int64_t* best_idx, double* best_val, double* best_x);
+/* ---- marginal-integration sweep: `_compute_marginals_int` (ext/CairoExt.jl:146-246), the heaviest batched caller of the
+ *      path.  lhc is the d x G Latin-hypercube sample matrix (host).  For every dimension k and grid value i (diagonal), and for
+ *      every pair a < b and grid values (ia, ib), row k (rows a, b) of lhc is overwritten with range(lb, ub; length = grid_size)
+ *      values, func = exp(closure selected by `which`) is evaluated on the G points and averaged: `mean(f(grid))`.
+ *      The (d*gs + C(d,2)*gs^2) * G query points are generated on the device; only the means come back:
+ *      diag[i + gs*k]  and  pairs[ia + gs*ib + gs*gs*pair]  with pairs ordered (1,2),(1,3),...,(d-1,d) as in the reference.
+ *      Un-normalised (normalize_prob_vals!, ext/CairoExt.jl:410-430, stays on the host).  diag or pairs may be NULL. ------ */
+int bosip_b200_marginals_int(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior, const double* lhc,
+                             int64_t G, int grid_size, const double* lb, const double* ub, unsigned which, double* diag,
+                             double* pairs);
 /* Materialise candidates index_offset.. of a PHILOX/GRID source into `out` (d x M, memory space `mem`). */
 int bosip_b200_candidates(bosip_b200_ctx* ctx, const bosip_b200_cand_src* src, int d, int64_t M,
                           int64_t index_offset, int mem, double* out);

@@ -316,6 +316,38 @@ def maxvar_argmax(log_post_var: np.ndarray, log_space: bool):
 
 
 # ----------------------------------------------------------------------------------------------
+# marginal-integration sweep: _compute_marginals_int, ext/CairoExt.jl:146-246 (un-normalised means)
+# ----------------------------------------------------------------------------------------------
+def marginals_int(f, lhc: np.ndarray, lb, ub, grid_size: int, diag=True, pairs=True):
+    """f: matrix closure X (d x G) -> length-G values (e.g. exp(log_post_mean)).  Restates the reference's loops: overwrite
+    row(s) of the LHC grid with the range value(s), ys[i] = mean(f(grid)), restore.  Returns (diag gs x d, pairs gs x gs x npairs)."""
+    grid = np.array(lhc, dtype=float)
+    d = grid.shape[0]
+    axes = [np.linspace(lb[k], ub[k], grid_size) for k in range(d)]
+    out_d = np.zeros((grid_size, d)) if diag else None
+    out_p = np.zeros((grid_size, grid_size, d * (d - 1) // 2)) if pairs else None
+    if diag:
+        for k in range(d):
+            tmp = grid[k].copy()
+            for i, x_ in enumerate(axes[k]):
+                grid[k] = x_
+                out_d[i, k] = np.mean(f(grid))
+            grid[k] = tmp
+    if pairs:
+        pi = 0
+        for a in range(d):
+            for b in range(a + 1, d):
+                ta, tb = grid[a].copy(), grid[b].copy()
+                for ib, xb in enumerate(axes[b]):
+                    for ia, xa in enumerate(axes[a]):
+                        grid[a] = xa; grid[b] = xb
+                        out_p[ia, ib, pi] = np.mean(f(grid))
+                grid[a] = ta; grid[b] = tb
+                pi += 1
+    return out_d, out_p
+
+
+# ----------------------------------------------------------------------------------------------
 # A.6 evidence: src/posterior/evidence.jl:19-24
 # ----------------------------------------------------------------------------------------------
 def evidence(log_post_vals: np.ndarray, log_prior_vals: np.ndarray) -> float:

@@ -336,3 +336,37 @@ def test_bi_hyperparameter_samples(bb, ctx):
             np.testing.assert_array_equal(r2[k], res[k])
     finally:
         ctx.set_chunk(0)
+
+
+@pytest.mark.parametrize("func,key", [("posterior_mean", "log_post_mean"), ("approx_posterior", "log_approx_post"), ("posterior_variance", "log_post_var")])
+def test_marginal_integration_sweep(bb, ctx, func, key):
+    """compute_marginals_int (ext/CairoExt.jl:146-246): device-generated sweep == the reference's overwrite-rows loop."""
+    pr, model, like, prior, ofit, olike, oprior = problem(bb, "X", d=3, p=2, N=90, seed=77)
+    prob = bb.BosipProblem(pr.X, pr.Y, model, like, prior, (pr.lb, pr.ub), ctx)
+    lhc = bb.generate_LHC((pr.lb, pr.ub), 37, np.random.default_rng(3))       # G = 37: not a divisor of anything
+    gs = 9
+    res = bb.compute_marginals_int(prob, func=func, grid_size=gs, xs=lhc, normalize=False)
+    f = lambda X: np.exp(orc.posterior_eval(ofit, olike, oprior, X)[key])
+    od, op = orc.marginals_int(f, lhc, pr.lb, pr.ub, gs)
+    tol = TOL if key != "log_post_var" else 1e-6
+    for k in range(3):
+        np.testing.assert_allclose(res["marginals"][(k, k)]["ys"], od[:, k], rtol=tol, atol=1e-300)
+    pi = 0
+    for a in range(3):
+        for b in range(a + 1, 3):
+            np.testing.assert_allclose(res["marginals"][(a, b)]["ys"], op[:, :, pi], rtol=tol, atol=1e-300)
+            np.testing.assert_array_equal(res["marginals"][(b, a)]["ys"], res["marginals"][(a, b)]["ys"].T)
+            pi += 1
+    # chunk boundaries never split a segment of G points
+    try:
+        ctx.set_chunk(128)
+        r2 = bb.compute_marginals_int(prob, func=func, grid_size=gs, xs=lhc, normalize=False)
+        for kk in res["marginals"]:
+            np.testing.assert_array_equal(r2["marginals"][kk]["ys"], res["marginals"][kk]["ys"])
+    finally:
+        ctx.set_chunk(0)
+    # normalisation (normalize_prob_vals!, ext/CairoExt.jl:410-430): trapezoid mass 1 on the plotting grid
+    rn = bb.compute_marginals_int(prob, func=func, grid_size=gs, xs=lhc)
+    step = (pr.ub - pr.lb) / (gs - 1)
+    ys = rn["marginals"][(0, 0)]["ys"]
+    assert (ys.sum() - 0.5 * (ys[0] + ys[-1])) * step[0] == pytest.approx(1.0, rel=1e-12)
