@@ -26,8 +26,11 @@ class GpOpts(C.Structure):
     _fields_ = [("jitter", C.c_double), ("pred_noise", C.c_int32), ("clamp_var", C.c_int32)]
 
 
+LIKE_NORMAL, LIKE_LOGNORMAL, LIKE_NORMAL_DIFF, LIKE_NORMAL_SUM, LIKE_EXP = 0, 1, 2, 3, 4
+
+
 class LikeNormal(C.Structure):
-    _fields_ = [("p", C.c_int32), ("z_obs", c_double_p), ("std_obs", c_double_p)]
+    _fields_ = [("p", C.c_int32), ("kind", C.c_int32), ("z_obs", c_double_p), ("std_obs", c_double_p), ("sum_lengths", c_int32_p)]
 
 
 class Prior(C.Structure):

@@ -178,11 +178,90 @@ class NormalLikelihood:
         if self.z_obs.shape != self.std_obs.shape:
             raise ValueError("z_obs and std_obs must have the same length")
 
+    @property
+    def obs_dim(self): return len(self.z_obs)
+    @property
+    def model_dim(self): return len(self.z_obs)
+
     def _c(self):
-        return L.LikeNormal(len(self.z_obs), _dptr(self.z_obs), _dptr(self.std_obs))
+        return L.LikeNormal(len(self.z_obs), L.LIKE_NORMAL, _dptr(self.z_obs), _dptr(self.std_obs), None)
 
 
 GaussianLikelihood = NormalLikelihood  # src/likelihoods/normal.jl:26
+
+
+@dataclass
+class LogNormalLikelihood:
+    """LogNormalLikelihood(; log_z_obs, CV) -- src/likelihoods/lognormal.jl:26-42; the model approximates log(y)."""
+    log_z_obs: np.ndarray
+    CV: np.ndarray
+
+    def __post_init__(self):
+        self.log_z_obs = np.ascontiguousarray(self.log_z_obs, dtype=np.float64)
+        self.CV = np.ascontiguousarray(self.CV, dtype=np.float64)
+        assert self.log_z_obs.shape == self.CV.shape
+
+    @property
+    def obs_dim(self): return len(self.log_z_obs)
+    @property
+    def model_dim(self): return len(self.log_z_obs)
+
+    def _c(self):
+        return L.LikeNormal(len(self.log_z_obs), L.LIKE_LOGNORMAL, _dptr(self.log_z_obs), _dptr(self.CV), None)
+
+
+@dataclass
+class NormalDiffLikelihood:
+    """NormalDiffLikelihood(; std_obs) -- src/likelihoods/normal_diff.jl:17-19; the model approximates |y - z_obs|."""
+    std_obs: np.ndarray
+
+    def __post_init__(self):
+        self.std_obs = np.ascontiguousarray(self.std_obs, dtype=np.float64)
+
+    @property
+    def obs_dim(self): return len(self.std_obs)
+    @property
+    def model_dim(self): return len(self.std_obs)
+
+    def _c(self):
+        return L.LikeNormal(len(self.std_obs), L.LIKE_NORMAL_DIFF, None, _dptr(self.std_obs), None)
+
+
+@dataclass
+class NormalSumLikelihood:
+    """NormalSumLikelihood(; sum_lengths, z_obs, std_obs) -- src/likelihoods/normal_sum.jl:18-27: every observation is the sum
+    of a contiguous group of model outputs."""
+    sum_lengths: np.ndarray
+    z_obs: np.ndarray
+    std_obs: np.ndarray
+
+    def __post_init__(self):
+        self.sum_lengths = np.ascontiguousarray(self.sum_lengths, dtype=np.int32)
+        self.z_obs = np.ascontiguousarray(self.z_obs, dtype=np.float64)
+        self.std_obs = np.ascontiguousarray(self.std_obs, dtype=np.float64)
+        assert len(self.sum_lengths) == len(self.z_obs), "sum_lengths and z_obs must have the same length"
+
+    @property
+    def obs_dim(self): return len(self.z_obs)
+    @property
+    def model_dim(self): return int(self.sum_lengths.sum())
+
+    def _c(self):
+        return L.LikeNormal(len(self.z_obs), L.LIKE_NORMAL_SUM, _dptr(self.z_obs), _dptr(self.std_obs),
+                            self.sum_lengths.ctypes.data_as(L.c_int32_p))
+
+
+@dataclass
+class ExpLikelihood:
+    """ExpLikelihood() -- src/likelihoods/exp.jl:7: the (single) model output is the log-likelihood itself."""
+
+    @property
+    def obs_dim(self): return 1
+    @property
+    def model_dim(self): return 1
+
+    def _c(self):
+        return L.LikeNormal(1, L.LIKE_EXP, None, None, None)
 
 
 @dataclass
@@ -426,7 +505,7 @@ def normal_likelihood_eval(like: NormalLikelihood, mu, var=None, outputs=_LIKE_O
     """NormalLikelihood algebra on the device for ANY ModelPosterior's (mu, var): p (vector) or p x M (matrix) inputs.
     Returns a dict with the requested outputs (marginal ones p / p x M, the others scalar / length M) + 'n_clamped'."""
     ctx = ctx or default_context()
-    p = len(like.z_obs)
+    p, nq = like.model_dim, like.obs_dim
     vec = (np.ndim(mu) == 1) if not _is_torch(mu) else (mu.dim() == 1)
     mu_m = mu.reshape(p, 1) if vec else mu
     kmu, pmu, mem, M = _colmajor(mu_m, p)
@@ -439,7 +518,7 @@ def normal_likelihood_eval(like: NormalLikelihood, mu, var=None, outputs=_LIKE_O
     res, ptrs = {}, []
     for name in _LIKE_OUTS:
         if name in outputs:
-            shape = (p, M) if name in ("loglike_marginal", "log_marginal_mean") else (M,)
+            shape = (nq, M) if name in ("loglike_marginal", "log_marginal_mean") else (M,)
             o, addr = _out(shape, mem, kmu); res[name] = o; ptrs.append(addr)
         else:
             ptrs.append(None)

@@ -71,22 +71,55 @@ int ensure_ws(Ctx* ctx, size_t bytes) {
   return 0;
 }
 
+int make_like_params(Ctx* ctx, const bosip_b200_like_normal* like, int gp_p, EpiParams* ep) {
+  const int q = like->p, kind = like->kind;
+  if (q < 1 || q > MAX_P) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood dimension out of range");
+  ep->like_kind = kind; ep->q = q; ep->c_approx = ep->c_mean = ep->c_sq = 0.0; ep->log_C = 0.0;
+  for (int i = 0; i < q; ++i) { ep->grp[i] = 1; ep->z[i] = 0.0; ep->so[i] = 1.0; }
+  if (kind == BOSIP_B200_LIKE_EXP) {  // src/likelihoods/exp.jl:9-16: exactly one model output
+    if (q != 1 || gp_p != 1) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "ExpLikelihood needs a single model output");
+    return 0;
+  }
+  if (kind < 0 || kind > BOSIP_B200_LIKE_EXP) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown likelihood kind");
+  if (!like->std_obs) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood needs std_obs");
+  if (kind != BOSIP_B200_LIKE_NORMAL_DIFF && !like->z_obs) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood needs z_obs");
+  int total = q;
+  if (kind == BOSIP_B200_LIKE_NORMAL_SUM) {
+    if (!like->sum_lengths) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "NormalSumLikelihood needs sum_lengths");
+    total = 0;
+    for (int i = 0; i < q; ++i) {
+      if (like->sum_lengths[i] < 1) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "sum_lengths must be >= 1");
+      ep->grp[i] = like->sum_lengths[i]; total += like->sum_lengths[i];
+    }
+  }
+  if (total != gp_p) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood dimension p does not match the GP's output dimension");
+  double logc = 0.0, sum_logz = 0.0;
+  for (int i = 0; i < q; ++i) {
+    double so = like->std_obs[i], z = (kind == BOSIP_B200_LIKE_NORMAL_DIFF) ? 0.0 : like->z_obs[i];
+    if (kind == BOSIP_B200_LIKE_LOGNORMAL) {
+      // sigma_log = sqrt(log(1 + CV^2)); mu_log = log_y - sigma_log^2/2 (lognormal.jl:44-45).  logpdf(LogNormal(mu_log, s), z)
+      // = logN(log z; log_y - sigma_log^2/2, s) - log z = logN(log z + sigma_log^2/2; log_y, s) - log z
+      if (!(so > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "CV must be > 0");
+      so = sqrt(log(1.0 + so * so));
+      sum_logz += z;
+      z = z + so * so / 2.0;
+    }
+    if (!(so > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "std_obs must be > 0");
+    ep->z[i] = z; ep->so[i] = so;
+    logc += log(2.0 * sqrt(M_PI) * so);  // src/likelihoods/normal.jl:75
+  }
+  ep->log_C = -logc;
+  if (kind == BOSIP_B200_LIKE_LOGNORMAL) { ep->c_approx = ep->c_mean = -sum_logz; ep->c_sq = -2.0 * sum_logz; }  // lognormal.jl:47-50,84
+  return 0;
+}
+
 static int make_epi(Ctx* ctx, const Gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior, EpiParams* ep) {
   memset(ep, 0, sizeof(*ep));
   ep->p = gp->p; ep->d = gp->d;
   ep->pred_noise = gp->opts.pred_noise; ep->clamp_var = gp->opts.clamp_var;
-  for (int j = 0; j < gp->p; ++j) { ep->kxx[j] = gp->alpha2[j]; ep->sig2[j] = gp->sig2[j]; ep->z[j] = 0.0; ep->so[j] = 1.0; }
-  if (like) {
-    if (like->p != gp->p) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood dimension p does not match the GP's output dimension");
-    if (!like->z_obs || !like->std_obs) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood needs z_obs and std_obs");
-    double logc = 0.0;
-    for (int j = 0; j < gp->p; ++j) {
-      if (!(like->std_obs[j] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "std_obs must be > 0");
-      ep->z[j] = like->z_obs[j]; ep->so[j] = like->std_obs[j];
-      logc += log(2.0 * sqrt(M_PI) * like->std_obs[j]);  // src/likelihoods/normal.jl:75
-    }
-    ep->log_C = -logc;
-  }
+  for (int j = 0; j < gp->p; ++j) { ep->kxx[j] = gp->alpha2[j]; ep->sig2[j] = gp->sig2[j]; ep->z[j] = 0.0; ep->so[j] = 1.0; ep->grp[j] = 1; }
+  ep->q = gp->p;
+  if (like) BOSIP_TRY(make_like_params(ctx, like, gp->p, ep));
   ep->has_prior = 0;
   if (prior) {
     if (prior->logprior) ep->has_prior = 2;
@@ -546,30 +579,27 @@ int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* h, const bosip_b200_like_n
                                       int64_t M, int mem, double* marg_approx, double* l_approx, double* marg_mean,
                                       double* l_mean, double* l_sq, double* l_var, int64_t* n_clamped) {
   API_LOCK(h);
-  if (!like || !like->z_obs || !like->std_obs || like->p < 1 || like->p > MAX_P) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad likelihood");
+  if (!like || like->p < 1 || like->p > MAX_P) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad likelihood");
   if (M < 0 || (!mu && M > 0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "mu is required");
   if (n_clamped) *n_clamped = 0;
   if (M == 0) return 0;
-  const int p = like->p;
   EpiParams ep; memset(&ep, 0, sizeof(ep));
+  int p = like->p;  // model-output dimension of mu / var
+  if (like->kind == BOSIP_B200_LIKE_NORMAL_SUM && like->sum_lengths) { p = 0; for (int i = 0; i < like->p; ++i) p += like->sum_lengths[i]; }
+  if (p < 1 || p > MAX_P) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad likelihood");
   ep.p = p;
-  double logc = 0.0;
-  for (int j = 0; j < p; ++j) {
-    if (!(like->std_obs[j] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "std_obs must be > 0");
-    ep.z[j] = like->z_obs[j]; ep.so[j] = like->std_obs[j];
-    logc += log(2.0 * sqrt(M_PI) * like->std_obs[j]);
-  }
-  ep.log_C = -logc;
+  BOSIP_TRY(make_like_params(ctx, like, p, &ep));
+  const int q = ep.q;
   cudaStream_t st = ctx->s_comp;
   const bool host = mem == BOSIP_B200_HOST;
-  const size_t pm = (size_t)p * M, mm = (size_t)M;
+  const size_t pm = (size_t)p * M, qm = (size_t)q * M, mm = (size_t)M;
   size_t off = 0;
   auto carve = [&](size_t n) { size_t o = off; off += (n * 8 + 255) / 256 * 256; return o; };
   const size_t o_cnt = carve(4);
   size_t o_mu = 0, o_var = 0, o_ma = 0, o_la = 0, o_mm = 0, o_lm = 0, o_ls = 0, o_lv = 0;
   if (host) {
     o_mu = carve(pm); if (var) o_var = carve(pm);
-    if (marg_approx) o_ma = carve(pm); if (l_approx) o_la = carve(mm); if (marg_mean) o_mm = carve(pm);
+    if (marg_approx) o_ma = carve(qm); if (l_approx) o_la = carve(mm); if (marg_mean) o_mm = carve(qm);
     if (l_mean) o_lm = carve(mm); if (l_sq) o_ls = carve(mm); if (l_var) o_lv = carve(mm);
   }
   BOSIP_TRY(ensure_ws(ctx, off));
@@ -586,9 +616,9 @@ int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* h, const bosip_b200_like_n
   }
   BOSIP_TRY(launch_like_eval(ctx, ep, dmu, dvar, M, dma, dla, dmm, dlm, dls, dlv, reinterpret_cast<unsigned long long*>(D(o_cnt)), st));
   if (host) {
-    if (marg_approx) BOSIP_CUDA(ctx, cudaMemcpyAsync(marg_approx, dma, pm * 8, cudaMemcpyDeviceToHost, st));
+    if (marg_approx) BOSIP_CUDA(ctx, cudaMemcpyAsync(marg_approx, dma, qm * 8, cudaMemcpyDeviceToHost, st));
     if (l_approx) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_approx, dla, mm * 8, cudaMemcpyDeviceToHost, st));
-    if (marg_mean) BOSIP_CUDA(ctx, cudaMemcpyAsync(marg_mean, dmm, pm * 8, cudaMemcpyDeviceToHost, st));
+    if (marg_mean) BOSIP_CUDA(ctx, cudaMemcpyAsync(marg_mean, dmm, qm * 8, cudaMemcpyDeviceToHost, st));
     if (l_mean) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_mean, dlm, mm * 8, cudaMemcpyDeviceToHost, st));
     if (l_sq) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_sq, dls, mm * 8, cudaMemcpyDeviceToHost, st));
     if (l_var) BOSIP_CUDA(ctx, cudaMemcpyAsync(l_var, dlv, mm * 8, cudaMemcpyDeviceToHost, st));

@@ -35,6 +35,10 @@ struct EpiParams {
   int pred_noise, clamp_var;
   double z[MAX_P], so[MAX_P], kxx[MAX_P], sig2[MAX_P];
   double log_C;             // -sum log(2 sqrt(pi) so_j)      (src/likelihoods/normal.jl:75)
+  int like_kind;            // BOSIP_B200_LIKE_*: 0..3 share the Gaussian-family formulas, 4 = ExpLikelihood
+  int q;                    // observation dims; observation i sums grp[i] consecutive GP outputs (1 except NormalSum)
+  int grp[MAX_P];
+  double c_approx, c_mean, c_sq;  // additive constants of the plug-in / E[l] / E[l^2] closures (LogNormal: -sum log z_obs terms)
   int prior_kind[MAX_D];
   double prior_prm[MAX_D][4];
   double prior_const[MAX_D];  // per-dimension additive constant (uniform: -log(b-a); truncnormal: -logtp)
@@ -144,6 +148,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // ------------------------------------------------------------------ cross-TU host entry points
 // api.cu: grow-only device workspace of the context (valid until the next call that needs a bigger one)
 int ensure_ws(Ctx* ctx, size_t bytes);
+// fill the likelihood part of the epilogue parameters (gp_p = GP output dimension the likelihood must match)
+int make_like_params(Ctx* ctx, const bosip_b200_like_normal* like, int gp_p, EpiParams* ep);
 // kstar.cu
 int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit,
                  int nspan, double* Ks, double* mu_part, bool write_k, cudaStream_t st);

@@ -63,25 +63,48 @@ epilogue_kernel(const __grid_constant__ EpiParams ep, const double* __restrict__
     else if (ep.has_prior == 1) lp = log_prior_point(ep, xq + m * ep.d);
   }
 
-  double plug = 0.0, lm = 0.0, lsq = 0.0;
-  for (int j = 0; j < p; ++j) {
-    double mu = 0.0;
-    for (int s = 0; s < nsplit; ++s) mu += mu_part[((size_t)s * p + j) * mc + m];
-    if (mean_at_xq) mu += mean_at_xq[m * p + j];
-    if (mu_out) mu_out[m * p + j] = mu;
-    const double z = ep.z[j], so = ep.so[j];
-    if (log_approx) plug += normlogpdf(mu, so, z);
-    if (have_var) {
-      double q = 0.0;
-      for (int t = 0; t < T; ++t) q += q_part[((size_t)t * p + j) * mc + m];
-      double var = ep.kxx[j] - q;
-      if (ep.pred_noise) var += ep.sig2[j];
-      if (ep.clamp_var && var < 0.0) var = 0.0;
-      if (var_out) var_out[m * p + j] = var;
-      const double so2 = so * so;
-      lm += normlogpdf(mu, sqrt(so2 + var), z);
-      lsq += normlogpdf(mu, sqrt((so2 + 2.0 * var) / 2.0), z);
+  // Observation i sums grp[i] consecutive model outputs (NormalSumLikelihood, src/likelihoods/normal_sum.jl:32-57; 1 otherwise).
+  double plug = ep.c_approx, lm = ep.c_mean, lsq = ep.c_sq;
+  double exp_mu = 0.0, exp_var = 0.0;  // ExpLikelihood: the single model output
+  int j = 0;
+  for (int i = 0; i < ep.q; ++i) {
+    double mu_i = 0.0, var_i = 0.0;
+    for (int gidx = 0; gidx < ep.grp[i]; ++gidx, ++j) {
+      double mu = 0.0;
+      for (int s = 0; s < nsplit; ++s) mu += mu_part[((size_t)s * p + j) * mc + m];
+      if (mean_at_xq) mu += mean_at_xq[m * p + j];
+      if (mu_out) mu_out[m * p + j] = mu;
+      mu_i += mu;
+      if (have_var) {
+        double q = 0.0;
+        for (int t = 0; t < T; ++t) q += q_part[((size_t)t * p + j) * mc + m];
+        double var = ep.kxx[j] - q;
+        if (ep.pred_noise) var += ep.sig2[j];
+        if (ep.clamp_var && var < 0.0) var = 0.0;
+        if (var_out) var_out[m * p + j] = var;
+        var_i += var;
+      }
     }
+    if (ep.like_kind == BOSIP_B200_LIKE_EXP) { exp_mu = mu_i; exp_var = var_i; continue; }
+    const double z = ep.z[i], so = ep.so[i];
+    if (log_approx) plug += normlogpdf(mu_i, so, z);
+    if (have_var) {
+      const double so2 = so * so;
+      lm += normlogpdf(mu_i, sqrt(so2 + var_i), z);
+      lsq += normlogpdf(mu_i, sqrt((so2 + 2.0 * var_i) / 2.0), z);
+    }
+  }
+  if (ep.like_kind == BOSIP_B200_LIKE_EXP) {
+    // src/likelihoods/exp.jl:9-16,19-33,50-63: loglike = y; log E[l] = mu + sigma^2/2; log V[l] = 2 (mu + sigma^2) + log(1 - exp(-sigma^2))
+    if (bi_mode == 0 && lp_out) lp_out[m] = lp;
+    const double lv = 2.0 * (exp_mu + exp_var) + log(1.0 - exp(-exp_var));
+    if (log_approx) log_approx[m] = bi_mode == 0 ? lp + exp_mu : (bi_mode == 1 ? exp(exp_mu) : log_approx[m] + exp(exp_mu));
+    if (have_var) {
+      const double lme = exp_mu + 0.5 * exp_var;
+      if (log_mean) log_mean[m] = bi_mode == 0 ? lp + lme : (bi_mode == 1 ? exp(lme) : log_mean[m] + exp(lme));
+      if (log_var) log_var[m] = bi_mode == 0 ? 2.0 * lp + lv : (bi_mode == 1 ? exp(lv) : log_var[m] + exp(lv));
+    }
+    return;
   }
   if (bi_mode == 0 && lp_out) lp_out[m] = lp;
   if (log_approx) log_approx[m] = bi_mode == 0 ? lp + plug : (bi_mode == 1 ? exp(plug) : log_approx[m] + exp(plug));
@@ -155,16 +178,30 @@ like_eval_kernel(const __grid_constant__ EpiParams ep, const double* __restrict_
                  double* __restrict__ l_var, unsigned long long* __restrict__ counters) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= m_valid) return;
-  const int p = ep.p;
-  double plug = 0.0, lm = 0.0, lsq = 0.0;
-  for (int j = 0; j < p; ++j) {
-    const double mu = mu_in[m * p + j], var = var_in ? var_in[m * p + j] : 0.0;
-    const double z = ep.z[j], so = ep.so[j], so2 = so * so;
+  const int p = ep.p, nq = ep.q;
+  if (ep.like_kind == BOSIP_B200_LIKE_EXP) {  // src/likelihoods/exp.jl
+    const double mu = mu_in[m], var = var_in ? var_in[m] : 0.0;
+    if (marg_approx) marg_approx[m] = mu;
+    if (marg_mean) marg_mean[m] = mu + 0.5 * var;
+    if (l_approx) l_approx[m] = mu;
+    if (l_mean) l_mean[m] = mu + 0.5 * var;
+    if (l_sq) l_sq[m] = 2.0 * mu + 2.0 * var;
+    if (l_var) l_var[m] = 2.0 * (mu + var) + log(1.0 - exp(-var));
+    return;
+  }
+  double plug = ep.c_approx, lm = ep.c_mean, lsq = ep.c_sq;
+  int j = 0;
+  for (int i = 0; i < nq; ++i) {
+    double mu = 0.0, var = 0.0;
+    for (int gidx = 0; gidx < ep.grp[i]; ++gidx, ++j) { mu += mu_in[m * p + j]; if (var_in) var += var_in[m * p + j]; }
+    const double z = ep.z[i], so = ep.so[i], so2 = so * so;
     const double t0 = normlogpdf(mu, so, z);
     const double t1 = normlogpdf(mu, sqrt(so2 + var), z);
     const double t2 = normlogpdf(mu, sqrt((so2 + 2.0 * var) / 2.0), z);
-    if (marg_approx) marg_approx[m * p + j] = t0;
-    if (marg_mean) marg_mean[m * p + j] = t1;
+    // per-dimension constant: LogNormal's -log z_obs_i = -(z'_i - so^2/2) (z' is the shifted log-observation)
+    const double ci = (ep.like_kind == BOSIP_B200_LIKE_LOGNORMAL) ? -(z - so2 / 2.0) : 0.0;
+    if (marg_approx) marg_approx[m * nq + i] = t0 + ci;
+    if (marg_mean) marg_mean[m * nq + i] = t1 + ci;
     plug += t0; lm += t1; lsq += t2;
   }
   if (l_approx) l_approx[m] = plug;

@@ -77,12 +77,26 @@ typedef struct {
   int32_t clamp_var;  /* 1: negative predictive variances are clamped to 0 before sqrt; default 1                 */
 } bosip_b200_gp_opts;
 
-/* NormalLikelihood(z_obs, std_obs): src/likelihoods/normal.jl:16-19 */
+/* Closed-form likelihoods of the Gaussian family (one fused epilogue serves them all):
+ *   NORMAL       NormalLikelihood(z_obs, std_obs)                 src/likelihoods/normal.jl:16-79
+ *   LOGNORMAL    LogNormalLikelihood(log_z_obs, CV)               src/likelihoods/lognormal.jl:26-91   (z_obs = log_z_obs, std_obs = CV)
+ *   NORMAL_DIFF  NormalDiffLikelihood(std_obs)                    src/likelihoods/normal_diff.jl:17-73 (z_obs ignored: 0)
+ *   NORMAL_SUM   NormalSumLikelihood(sum_lengths, z_obs, std_obs) src/likelihoods/normal_sum.jl:18-115 (contiguous groups of GP outputs are summed)
+ *   EXP          ExpLikelihood()                                  src/likelihoods/exp.jl:7-63          (the single GP output IS the log-likelihood)
+ * `p` is the number of OBSERVATION dimensions (NORMAL_SUM: number of sums; the GP has sum(sum_lengths) outputs; EXP: 1). */
+#define BOSIP_B200_LIKE_NORMAL 0
+#define BOSIP_B200_LIKE_LOGNORMAL 1
+#define BOSIP_B200_LIKE_NORMAL_DIFF 2
+#define BOSIP_B200_LIKE_NORMAL_SUM 3
+#define BOSIP_B200_LIKE_EXP 4
 typedef struct {
   int32_t p;
-  const double* z_obs;   /* p */
-  const double* std_obs; /* p, > 0 */
+  int32_t kind;               /* BOSIP_B200_LIKE_* (0 = NormalLikelihood) */
+  const double* z_obs;        /* p   (LOGNORMAL: log_z_obs; NORMAL_DIFF, EXP: may be NULL) */
+  const double* std_obs;      /* p, > 0 (LOGNORMAL: CV; EXP: may be NULL) */
+  const int32_t* sum_lengths; /* NORMAL_SUM: p group sizes; otherwise NULL */
 } bosip_b200_like_normal;
+typedef bosip_b200_like_normal bosip_b200_like;
 
 /* Product prior descriptor, or host-supplied log-prior values. */
 typedef struct {

@@ -18,7 +18,7 @@ const WANT_APPROX, WANT_MEAN, WANT_VAR = Cuint(1), Cuint(2), Cuint(4)
 const EDOMAIN, ENOTPD = Cint(-4), Cint(-3)
 
 struct GpOpts;  jitter::Cdouble; pred_noise::Int32; clamp_var::Int32; end
-struct LikeNormal; p::Int32; z_obs::Ptr{Cdouble}; std_obs::Ptr{Cdouble}; end
+struct LikeNormal; p::Int32; kind::Int32; z_obs::Ptr{Cdouble}; std_obs::Ptr{Cdouble}; sum_lengths::Ptr{Int32}; end  # kind: 0 Normal, 1 LogNormal, 2 NormalDiff, 3 NormalSum, 4 Exp
 struct Prior; d::Int32; kind::Ptr{Int32}; params::Ptr{Cdouble}; logprior::Ptr{Cdouble}; end
 struct CandSrc; kind::Int32; mem::Int32; points::Ptr{Cdouble}; seed::UInt64; lb::Ptr{Cdouble}; ub::Ptr{Cdouble}; n_per_dim::Int64; end
 
@@ -105,7 +105,7 @@ function _posterior_eval(post::B200GPPosterior, like::NormalLikelihood, x_prior,
     z, so = like.z_obs, like.std_obs
     ncl = Ref{Int64}(0)
     GC.@preserve Xc out kinds prm lp z so begin
-        lk = Ref(LikeNormal(length(z), pointer(z), pointer(so)))
+        lk = Ref(LikeNormal(length(z), 0, pointer(z), pointer(so), C_NULL))
         pr = Ref(Prior(post.d, isempty(kinds) ? C_NULL : pointer(kinds), isempty(prm) ? C_NULL : pointer(prm), lp === C_NULL ? C_NULL : pointer(lp)))
         check(post.ctx, ccall((:bosip_b200_posterior_eval, LIB), Cint,
             (Ptr{Cvoid}, Ref{LikeNormal}, Ref{Prior}, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Cuint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Int64}),
@@ -149,7 +149,7 @@ function BOSS.maximize_acquisition(am::B200CandidateAM, problem::BOSS.BossProble
         M = isnothing(am.candidates) ? am.count : size(am.candidates, 2)
         check(post.ctx, ccall((:bosip_b200_acq_argmax, LIB), Cint,
             (Ptr{Cvoid}, Ref{LikeNormal}, Ref{Prior}, Ref{CandSrc}, Int64, Int64, Cint, Ref{Int64}, Ref{Cdouble}, Ptr{Cdouble}),
-            post.h, Ref(LikeNormal(length(z), pointer(z), pointer(so))), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)),
+            post.h, Ref(LikeNormal(length(z), 0, pointer(z), pointer(so), C_NULL)), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)),
             Ref(src), M, 0, acq, best_idx, best_val, best_x))
     end
     return best_x, best_val[]   # BOSS 0.6 return convention (x vs (x, val)) to be confirmed -- SURVEY.md Appendix B item 6

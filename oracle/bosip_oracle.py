@@ -224,6 +224,100 @@ def log_likelihood_variance(like, mu, std):
 
 
 # ----------------------------------------------------------------------------------------------
+# The other closed-form likelihoods of the Gaussian family.  Each exposes the same three reductions as NormalLikelihood:
+#   loglike(mu)                         plug-in log-likelihood      (scalar / length M)
+#   log_likelihood_mean(mu, std)        log E[l]
+#   log_likelihood_variance(mu, std)    log V[l]   (via log E[l^2] and the clamp of src/posterior/likelihood.jl:47-65)
+# through `like_terms(like, mu, var)` below.
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class LogNormalLikelihood:
+    """src/likelihoods/lognormal.jl:26-91"""
+    log_z_obs: np.ndarray
+    CV: np.ndarray
+
+    def __post_init__(self):
+        self.log_z_obs = np.asarray(self.log_z_obs, float); self.CV = np.asarray(self.CV, float)
+        self.z_obs = np.exp(self.log_z_obs)                       # :34
+        self.sigma_log = np.sqrt(np.log(1.0 + self.CV ** 2))      # :45
+
+
+@dataclass
+class NormalDiffLikelihood:
+    """src/likelihoods/normal_diff.jl:17-73"""
+    std_obs: np.ndarray
+
+    def __post_init__(self):
+        self.std_obs = np.asarray(self.std_obs, float)
+
+
+@dataclass
+class NormalSumLikelihood:
+    """src/likelihoods/normal_sum.jl:18-115"""
+    sum_lengths: Sequence[int]
+    z_obs: np.ndarray
+    std_obs: np.ndarray
+
+    def __post_init__(self):
+        self.z_obs = np.asarray(self.z_obs, float); self.std_obs = np.asarray(self.std_obs, float)
+
+
+@dataclass
+class ExpLikelihood:
+    """src/likelihoods/exp.jl:7-63"""
+
+
+def _lognormal_logpdf(mu_log, s, z):
+    """Distributions.logpdf(LogNormal(mu, s), z) = normlogpdf(mu, s, log z) - log z"""
+    return normlogpdf(mu_log, s, np.log(z)) - np.log(z)
+
+
+def _indexed_sum(Y, sum_lengths):
+    """_indexed_sum (src/likelihoods/normal_sum.jl:29-40) over the leading axis."""
+    out, idx = [], 0
+    for n in sum_lengths:
+        out.append(Y[idx:idx + n].sum(axis=0)); idx += n
+    return np.stack(out)
+
+
+def like_terms(like, mu, var):
+    """mu, var: p (vector) or p x M.  Returns dict(loglike_marginal, loglike, log_marginal_mean, log_like_mean, log_sq_like_mean,
+    log_like_var) restating the per-likelihood reference code cited in the class docstrings."""
+    mu = np.asarray(mu, float); var = np.zeros_like(mu) if var is None else np.asarray(var, float)
+    col = (lambda v: v) if mu.ndim == 1 else (lambda v: np.asarray(v)[:, None])
+    if isinstance(like, ExpLikelihood):                                     # exp.jl:9-16, 19-33, 50-63
+        m, v = mu[0], var[0]
+        with np.errstate(divide="ignore"):
+            return {"loglike_marginal": mu, "loglike": m, "log_marginal_mean": mu + 0.5 * var, "log_like_mean": m + 0.5 * v,
+                    "log_sq_like_mean": 2 * m + 2 * v, "log_like_var": 2 * (m + v) + np.log(1 - np.exp(-v))}
+    if isinstance(like, LogNormalLikelihood):
+        z, s0 = col(like.z_obs), col(like.sigma_log)
+        mu_log = mu - s0 ** 2 / 2                                           # lognormal.jl:44
+        lmarg = _lognormal_logpdf(mu_log, s0, z)                            # :47-50
+        mmarg = _lognormal_logpdf(mu_log, np.sqrt(s0 ** 2 + var), z)        # :56-61
+        log_C = -np.sum(np.log(2 * math.sqrt(math.pi) * like.sigma_log * like.z_obs))              # :83
+        lsq = log_C + _lognormal_logpdf(mu_log, np.sqrt((s0 ** 2 + 2 * var) / 2), z).sum(axis=0)   # :81-84
+    else:
+        if isinstance(like, NormalSumLikelihood):
+            mu = _indexed_sum(mu, like.sum_lengths); var = _indexed_sum(var, like.sum_lengths)     # normal_sum.jl:42-46
+            z, s0 = col(like.z_obs), col(like.std_obs)
+        elif isinstance(like, NormalDiffLikelihood):
+            z, s0 = col(np.zeros_like(like.std_obs)), col(like.std_obs)                            # normal_diff.jl:21-23
+        else:
+            z, s0 = col(like.z_obs), col(like.std_obs)
+        lmarg = normlogpdf(mu, s0, z)
+        mmarg = normlogpdf(mu, np.sqrt(s0 ** 2 + var), z)
+        log_C = -np.sum(np.log(2 * math.sqrt(math.pi) * np.ravel(s0)))
+        lsq = log_C + normlogpdf(mu, np.sqrt((s0 ** 2 + 2 * var) / 2), z).sum(axis=0)
+    lmean = mmarg.sum(axis=0)
+    v = assure_nonneg(np.exp(lsq) - np.exp(2.0 * lmean))                    # src/posterior/likelihood.jl:55-57
+    with np.errstate(divide="ignore"):
+        lvar = np.log(v)
+    return {"loglike_marginal": lmarg, "loglike": lmarg.sum(axis=0), "log_marginal_mean": mmarg, "log_like_mean": lmean,
+            "log_sq_like_mean": lsq, "log_like_var": lvar}
+
+
+# ----------------------------------------------------------------------------------------------
 # A.5 priors and posterior closures: src/posterior/log_posterior.jl
 # ----------------------------------------------------------------------------------------------
 UNIFORM, NORMAL, TRUNCNORMAL = 0, 1, 2

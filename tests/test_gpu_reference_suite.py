@@ -188,3 +188,97 @@ def test_domain_error_like_the_reference(env):  # src/posterior/likelihood.jl:61
     # tiny negative values clamp to zero -> -Inf, counted
     r = bb.normal_likelihood_eval(bb.NormalLikelihood([0.0], [1.0]), np.array([[30.0]]), np.array([[-1e-12]]), ("log_like_var",))
     assert r["log_like_var"][0] == -np.inf
+
+
+# ======================================================================================================================
+# The other closed-form likelihoods: test/unit/test/likelihoods/{lognormal,normal_diff,
+# normal_sum,exp}.jl re-run through the C ABI with the same fixtures + random parity against the oracle restatements.
+# ======================================================================================================================
+def _family_cases(bb):
+    rng = np.random.default_rng(11)
+    return [
+        ("lognormal", bb.LogNormalLikelihood([0.0, 0.5, 1.0], [0.1, 0.2, 0.1]), orc.LogNormalLikelihood([0.0, 0.5, 1.0], [0.1, 0.2, 0.1]),
+         np.array([0.1, 0.6, 1.1])),                                                         # lognormal.jl:1-13
+        ("normal_diff", bb.NormalDiffLikelihood([0.5, 1.0, 2.0]), orc.NormalDiffLikelihood([0.5, 1.0, 2.0]), np.array([0.1, 0.2, 0.3])),
+        ("normal_sum", bb.NormalSumLikelihood([2, 1, 3], [1.0, 2.0, 3.0], [0.5, 1.0, 2.0]), orc.NormalSumLikelihood([2, 1, 3], [1.0, 2.0, 3.0], [0.5, 1.0, 2.0]),
+         rng.normal(0.5, 0.3, 6)),
+        ("exp", bb.ExpLikelihood(), orc.ExpLikelihood(), np.array([2.5])),                   # exp.jl:1-4
+    ]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_likelihood_family_fixture_tests(env, idx):
+    bb = env[0]
+    name, like, olike, y = _family_cases(bb)[idx]
+    p = len(y)
+    var = np.full(p, 0.25) if name != "lognormal" else olike.sigma_log ** 2          # lognormal.jl:52-53, exp.jl:17-19
+    post_zero, post_nonzero = MockModelPosterior(y, np.zeros(p)), MockModelPosterior(y, var)
+    X3 = np.array([[0.0, 1.0, 2.0]])
+    # loglike_marginal / loglike, vector and matrix methods + consistency
+    Y = np.stack([y, y - 0.2], axis=1)
+    lm, l = bb.loglike_marginal(like, y), bb.loglike(like, y)
+    ot = orc.like_terms(olike, y, None)
+    np.testing.assert_allclose(lm, ot["loglike_marginal"], rtol=RTOL)
+    assert isinstance(l, float) and l == pytest.approx(float(ot["loglike"]), rel=RTOL)
+    Lm = bb.loglike_marginal(like, Y)
+    assert Lm.shape == (like.obs_dim, 2)
+    np.testing.assert_allclose(Lm[:, 0], lm, rtol=RTOL)
+    np.testing.assert_allclose(Lm.sum(0), bb.loglike(like, Y), rtol=RTOL)
+    assert lm.sum() == pytest.approx(l, rel=RTOL)
+    # expectations: zero variance == plug-in, nonzero matches the closed form, matrix == columnwise, marginal/sum consistency
+    f_zero, f_non = bb.log_marginal_likelihood_mean(like, post_zero), bb.log_marginal_likelihood_mean(like, post_nonzero)
+    np.testing.assert_allclose(f_zero(x), lm, rtol=RTOL)
+    on = orc.like_terms(olike, y, var)
+    np.testing.assert_allclose(f_non(x), on["log_marginal_mean"], rtol=RTOL)
+    assert not np.allclose(f_non(x), f_zero(x))
+    Rm = f_non(X3)
+    assert Rm.shape == (like.obs_dim, 3)
+    for i in range(3):
+        np.testing.assert_allclose(Rm[:, i], f_non(X3[:, i]), rtol=RTOL)
+    g = bb.log_likelihood_mean(like, post_nonzero)
+    assert g(x) == pytest.approx(float(on["log_like_mean"]), rel=RTOL)
+    np.testing.assert_allclose(Rm.sum(0), g(X3), rtol=RTOL)
+    # variance: type/shape/self-consistency as the reference checks it, plus the oracle's number
+    h = bb.log_likelihood_variance(like, post_nonzero)
+    assert isinstance(h(x), float)
+    hv = h(X3)
+    assert hv.shape == (3,)
+    for i in range(3):
+        assert hv[i] == pytest.approx(h(X3[:, i]), rel=RTOL)
+    assert h(x) == pytest.approx(float(on["log_like_var"]), rel=1e-9)
+    if name == "exp":                                                                   # exp.jl:22-46
+        assert bb.log_likelihood_mean(like, post_zero)(x) == pytest.approx(2.5, rel=RTOL)
+        assert g(x) == pytest.approx(2.5 + 0.5 * 0.25, rel=RTOL) and g(x) > bb.log_likelihood_mean(like, post_zero)(x)
+        assert np.exp(h(x)) > 0
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_likelihood_family_random_parity_and_gp_path(env, ctx, idx):
+    bb = env[0]
+    name, like, olike, y = _family_cases(bb)[idx]
+    rng = np.random.default_rng(40 + idx)
+    p, M = like.model_dim, 3000
+    mu = rng.normal(float(np.mean(y)), 0.4, (p, M)); var = rng.uniform(0.0, 0.5, (p, M)); var[:, :50] = 0.0
+    r = bb.normal_likelihood_eval(like, mu, var)
+    o = orc.like_terms(olike, mu, var)
+    for k in ("loglike_marginal", "loglike", "log_marginal_mean", "log_like_mean", "log_sq_like_mean"):
+        np.testing.assert_allclose(r[k], o[k], rtol=RTOL, atol=1e-13)
+    fin = np.isfinite(o["log_like_var"]) & (var.min(0) > 1e-3)
+    np.testing.assert_allclose(r["log_like_var"][fin], o["log_like_var"][fin], rtol=1e-8)
+    # the fused GP path with this likelihood == GP predict (oracle) + the likelihood restatement + prior
+    pr = bb.synth.make_problem("X", d=2, p=p, N=60, seed=900 + idx)
+    model = bb.GaussianProcess(pr.kernel_id, pr.lam, 0.3 * pr.alpha, 0.3 * pr.sigma)
+    Ysc = 0.3 * pr.Y + float(np.mean(y))
+    post = bb.model_posterior(model, pr.X, Ysc, ctx=ctx)
+    ofit = orc.gp_fit(pr.kernel_id, pr.X, Ysc, pr.lam, 0.3 * pr.alpha, 0.3 * pr.sigma)
+    prior = bb.ProductPrior(pr.prior_kind, pr.prior_params); oprior = orc.ProductPrior(list(pr.prior_kind), [list(q) for q in pr.prior_params])
+    Xq = rng.uniform(pr.lb[:, None], pr.ub[:, None], size=(2, 2000))
+    res = bb.posterior_eval(post, like, prior, Xq, 7)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    ot = orc.like_terms(olike, omu, ovar); lp = orc.log_prior(oprior, Xq)
+    np.testing.assert_allclose(res["log_approx_post"], lp + ot["loglike"], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(res["log_post_mean"], lp + ot["log_like_mean"], rtol=RTOL, atol=1e-12)
+    ref = 2 * lp + ot["log_like_var"]
+    fin = np.isfinite(ref) & np.isfinite(res["log_post_var"])
+    assert fin.mean() > 0.9
+    assert np.all(np.abs(res["log_post_var"][fin] - ref[fin]) <= 1e-10 * np.abs(ref[fin]) + 1e-6)
