@@ -13,6 +13,6 @@ from .api import (B200CandidateAM, B200GPPosterior, BosipB200Error, BosipProblem
                   log_posterior_mean, log_posterior_variance, model_posterior, model_posterior_from_factors,
                   posterior_eval, posterior_mean, posterior_variance, normal_likelihood_eval, loglike, loglike_marginal,
                   log_approx_marginal_likelihood, log_marginal_likelihood_mean, log_sq_likelihood_mean, compute_marginals_int,
-                  generate_LHC, normalize_prob_vals, LogNormalLikelihood, NormalDiffLikelihood, NormalSumLikelihood, ExpLikelihood)
+                  generate_LHC, normalize_prob_vals, LogNormalLikelihood, NormalDiffLikelihood, NormalSumLikelihood, ExpLikelihood, bosip, DataLimit, IterLimit)
 
 __version__ = "0.1.0"

@@ -881,3 +881,53 @@ def compute_marginals_int(bosip: BosipProblem, func: str = "posterior_mean", gri
                 marg[(b, a)] = {"xs": (axes[b], axes[a]), "ys": ys.T}
                 pi += 1
     return {"marginals": marg, "bounds": (lb, ub), "X": bosip.X, "lhc": xs}
+
+
+# ----------------------------------------------------------------------------------------------- the BO loop (bosip!)
+@dataclass
+class DataLimit:
+    """BOSS.DataLimit(n): stop when the dataset holds n simulations (examples/simple/main.jl:63)."""
+    n: int
+
+    def __call__(self, problem: BosipProblem) -> bool:
+        return problem.X.shape[1] < self.n
+
+
+@dataclass
+class IterLimit:
+    """BOSS.IterLimit(n)."""
+    n: int
+    _it: int = 0
+
+    def __call__(self, problem: BosipProblem) -> bool:
+        self._it += 1
+        return self._it <= self.n
+
+
+def bosip(problem: BosipProblem, simulator: Callable, acquisition=None, acq_maximizer: Optional[B200CandidateAM] = None,
+          term_cond=None, model_fitter: Optional[Callable] = None, callback: Optional[Callable] = None, info: bool = False):
+    """bosip!(bosip; model_fitter, acq_maximizer, term_cond, options) -- src/main.jl:43-64, the loop BOSS.bo! runs:
+    [estimate parameters] -> maximise the acquisition over the candidate set -> evaluate the simulator -> augment the data.
+
+    Only the acquisition step is this repository's business (fused evaluate + argmax on the device); `model_fitter`
+    (problem -> GaussianProcess with new hyper-parameters, BOSS's MAP/BI fit) is an optional host callback and defaults to
+    keeping the current hyper-parameters."""
+    acquisition = acquisition or MaxVar()
+    term_cond = term_cond or IterLimit(1)
+    if acq_maximizer is None:
+        lb, ub = problem.bounds
+        acq_maximizer = B200CandidateAM(CandidateSource.philox(0, lb, ub, 100_000))
+    it = 0
+    while term_cond(problem):
+        if model_fitter is not None:
+            problem.model = model_fitter(problem)
+            problem.augment(np.empty((problem.X.shape[0], 0)), np.empty((problem.Y.shape[0], 0)))  # drop the cached posterior
+        x, val = acq_maximizer.maximize_acquisition(problem, acquisition)
+        y = np.asarray(simulator(x), dtype=np.float64).reshape(-1)
+        problem.augment(x, y)
+        it += 1
+        if info:
+            print(f"[bosip] iter {it}: x = {np.round(x, 4)}, acq = {val:.4g}, data = {problem.X.shape[1]}")
+        if callback is not None:
+            callback(problem, it, x, val)
+    return problem

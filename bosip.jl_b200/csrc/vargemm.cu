@@ -255,11 +255,8 @@ vargemm_kernel(const double* __restrict__ Ks, const double* __restrict__ LinvT, 
 }
 
 int launch_vargemm(Ctx* ctx, const Gp* gp, const double* Ks, int64_t mc, int64_t m_tiles, double* q_part, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VG_SMEM));
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and a process may hold contexts on several GPUs
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VG_SMEM));
   const int groups = (int)(m_tiles * gp->p);
   const int grid = groups < ctx->sms ? groups : ctx->sms;
   static const bool noimax = getenv("BOSIP_VG_NOIMAX") != nullptr;  // dev A/B switch
