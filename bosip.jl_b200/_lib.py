@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbosip_b200.so")
+LIB_PATH = os.environ.get("BOSIP_B200_LIB", os.path.join(HERE, "libbosip_b200.so"))  # env override: development A/B builds only
 
 OK, EINVAL, ECUDA, ENOTPD, EDOMAIN, ENOMEM = 0, -1, -2, -3, -4, -5
 SE, MATERN32, MATERN52 = 0, 1, 2

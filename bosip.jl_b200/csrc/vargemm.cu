@@ -26,10 +26,19 @@
 
 namespace bosip {
 
-constexpr int VG_STAGES = 5;
+#ifndef BOSIP_VG_STAGES
+#define BOSIP_VG_STAGES 5
+#endif
+#ifndef BOSIP_VG_RING
+#define BOSIP_VG_RING 12
+#endif
+#ifndef BOSIP_VG_LAG
+#define BOSIP_VG_LAG 2
+#endif
+constexpr int VG_STAGES = BOSIP_VG_STAGES;
 constexpr int VG_CONSUMER_WARPS = 8;
 constexpr int VG_THREADS = VG_CONSUMER_WARPS * 32;  // exactly 2 warps per SM sub-partition: up to 255 registers/thread
-constexpr int VG_LAG = 2;                           // the refill of a stage trails its release by this many chunks
+constexpr int VG_LAG = BOSIP_VG_LAG;                           // the refill of a stage trails its release by this many chunks
 constexpr int VG_STAGE_DOUBLES = (TILE_M + TILE_N) * TILE_K;  // A then B
 constexpr int VG_SUB = TILE_N / 8;                            // 16 n-subtiles of 8 columns
 constexpr size_t VG_SMEM = (size_t)VG_STAGES * VG_STAGE_DOUBLES * sizeof(double) + 2 * VG_STAGES * sizeof(uint64_t);
@@ -58,7 +67,7 @@ struct VgSched {  // compile-time schedule of the (k-step, subtile) pairs of one
   static __host__ __device__ constexpr int i_of(int q) { return imin(ks_of(q)) + q - first(ks_of(q)); }
 };
 
-constexpr int VG_RING = 12;  // B fragments in flight per thread (look-ahead of 11 pairs = 22 DMMAs = 352 pipe cycles)
+constexpr int VG_RING = BOSIP_VG_RING;  // B fragments in flight per thread (look-ahead of 11 pairs = 22 DMMAs = 352 pipe cycles)
 
 template <int DIAG_C, int IMAX>
 __device__ __forceinline__ void vg_chunk_fast(double (&c)[VG_SUB][4], uint32_t sbase, uint32_t a_off0b, uint32_t a_off1b,
