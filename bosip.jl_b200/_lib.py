@@ -16,6 +16,7 @@ WANT_APPROX, WANT_MEAN, WANT_VAR = 1, 2, 4
 ACQ_MAXVAR, ACQ_LOGMAXVAR = 0, 1
 PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_TRUNCNORMAL = 0, 1, 2
 CAND_POINTS, CAND_PHILOX, CAND_GRID = 0, 1, 2
+VAR_FP64, VAR_INT8 = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -51,6 +52,8 @@ PROTOTYPES = {
     "bosip_b200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bosip_b200_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
     "bosip_b200_set_chunk": (C.c_int, [C.c_void_p, C.c_int64]),
+    "bosip_b200_set_variance_engine": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bosip_b200_int8_peak": (C.c_int, [C.c_void_p, c_double_p]),
     "bosip_b200_gp_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                     c_double_p, c_double_p, c_double_p, C.POINTER(GpOpts), C.POINTER(C.c_void_p)]),
     "bosip_b200_gp_load_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,

@@ -128,6 +128,17 @@ class Context:
     def set_chunk(self, max_points: int):
         self._check(self.lib.bosip_b200_set_chunk(self.h, int(max_points)))
 
+    def set_variance_engine(self, engine: str = "fp64", slices: int = 0):
+        """'fp64' (DMMA) or 'int8' (tcgen05 INT8 on error-free byte slices; `slices` in 6..8, 0 = 7)."""
+        code = {"fp64": L.VAR_FP64, "int8": L.VAR_INT8}[engine]
+        self._check(self.lib.bosip_b200_set_variance_engine(self.h, code, int(slices)))
+
+    def int8_peak(self) -> float:
+        """Measured tcgen05 INT8 issue-rate ceiling (TOPS, 2 ops per MAC) of this GPU: the INT8 engine's roofline denominator."""
+        a = C.c_double()
+        self._check(self.lib.bosip_b200_int8_peak(self.h, C.byref(a)))
+        return a.value
+
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.bosip_b200_fp64_peak(self.h, C.byref(a), C.byref(b)))

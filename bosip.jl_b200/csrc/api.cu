@@ -196,10 +196,20 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   nspan = (int)round_up((Ns + nsplit - 1) / nsplit, 16);
   nsplit = (Ns + nspan - 1) / nspan;
 
+  // ---- variance engine (FP64 DMMA or INT8 tcgen05 with error-free slicing)
+  const bool i8 = sw.need_var && ctx->var_engine == BOSIP_B200_VAR_INT8;
+  const int S8 = ctx->var_slices, KB8 = (gp->N + 127) / 128;
+  int nsub8 = 1;
+  if (i8) {
+    for (Gp* gf : sw.fits) BOSIP_TRY(i8_prepare(ctx, gf, S8, ctx->s_comp));
+    nsub8 = i8_nsub(gp);
+  }
+
   // ---- chunk size
   int64_t mc;
   if (sw.need_var) {
-    const int64_t by_mem = (int64_t)(3.0e9 / ((double)p * Ns * 8.0)) / TILE_M * TILE_M;
+    const double k_bytes_per_point = i8 ? (double)p * KB8 * 128.0 * S8 : (double)p * Ns * 8.0;
+    const int64_t by_mem = (int64_t)(3.0e9 / k_bytes_per_point) / TILE_M * TILE_M;
     mc = std::min<int64_t>((int64_t)ctx->sms * TILE_M * 4, std::max<int64_t>(TILE_M, by_mem));
   } else {
     mc = (int64_t)ctx->sms * TILE_M * 16;
@@ -213,9 +223,10 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   // ---- workspace carve-up (all sizes in doubles, 256-byte aligned pieces)
   size_t off = 0;
   auto carve = [&](size_t n_doubles) { size_t o = off; off += (n_doubles * 8 + 255) / 256 * 256; return o; };
-  const size_t o_Ks = sw.need_var ? carve((size_t)p * Ns * mc) : 0;
+  const size_t o_Ks = sw.need_var ? carve(i8 ? (size_t)p * (mc / TILE_M) * KB8 * S8 * 2048 : (size_t)p * Ns * mc) : 0;
   const size_t o_mu_part = carve((size_t)nsplit * p * mc);
   const size_t o_q_part = sw.need_var ? carve((size_t)p * mc) : 0;
+  const size_t o_q_scr = i8 ? carve((size_t)nsub8 * p * mc) : 0;
   const bool stage_x = host || gen;
   size_t o_x[2] = {0, 0}, o_mean[2] = {0, 0}, o_lpin[2] = {0, 0}, o_mu[2] = {0, 0}, o_var[2] = {0, 0}, o_la[2] = {0, 0},
          o_lm[2] = {0, 0}, o_lv[2] = {0, 0}, o_lp[2] = {0, 0};
@@ -291,11 +302,16 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     for (int f = 0; f < n_fits; ++f) {
       Gp* gf = sw.fits[f];
       t_begin(ctx, 0, sc);
-      BOSIP_TRY(launch_kstar(ctx, gf, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var, sc));
+      BOSIP_TRY(launch_kstar(ctx, gf, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var ? (i8 ? 2 : 1) : 0, S8, sc));
       t_end(ctx, sc);
       if (sw.need_var) {
         t_begin(ctx, 1, sc);
-        BOSIP_TRY(launch_vargemm(ctx, gf, Ks, mc, m_tiles, q_part, sc));
+        if (i8) {
+          BOSIP_TRY(launch_vargemm_i8(ctx, gf, reinterpret_cast<const uint8_t*>(Ks), mc, m_tiles, D(o_q_scr), q_part, sc));
+          ctx->launches += 1;
+        } else {
+          BOSIP_TRY(launch_vargemm(ctx, gf, Ks, mc, m_tiles, q_part, sc));
+        }
         t_end(ctx, sc);
       }
       t_begin(ctx, 2, sc);
@@ -424,6 +440,15 @@ int bosip_b200_launch_count(bosip_b200_ctx* h, int64_t* out) {
   API_LOCK(h);
   if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
   *out = ctx->launches;
+  return 0;
+}
+
+int bosip_b200_set_variance_engine(bosip_b200_ctx* h, int engine, int slices) {
+  API_LOCK(h);
+  if (engine != BOSIP_B200_VAR_FP64 && engine != BOSIP_B200_VAR_INT8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown variance engine");
+  if (slices == 0) slices = 7;
+  if (slices < 6 || slices > 8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "slices must be 6, 7 or 8 (0 = default)");
+  ctx->var_engine = engine; ctx->var_slices = slices;
   return 0;
 }
 
@@ -783,6 +808,12 @@ int bosip_b200_tv(bosip_b200_ctx* h, const double* lw, const double* a, const do
   const double lme = isinf(s2[0]) ? s2[0] : s2[0] + log(s2[1]) - lg;
   *tv_out = 0.5 * exp(lme);
   return 0;
+}
+
+int bosip_b200_int8_peak(bosip_b200_ctx* h, double* tops) {
+  API_LOCK(h);
+  if (!tops) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "tops must not be NULL");
+  return i8_peak(ctx, tops);
 }
 
 int bosip_b200_fp64_peak(bosip_b200_ctx* h, double* dmma, double* dfma) {

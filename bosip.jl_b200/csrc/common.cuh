@@ -57,6 +57,11 @@ struct Gp {
   double* Linv = nullptr;   // [p][N][N] col-major L^{-1}
   double* a = nullptr;      // [p][N]
   double alpha2[MAX_P], sig2[MAX_P];
+  // INT8 variance engine (vargemm_i8.cu), built on first use from Linv
+  int i8_S = 0, i8_T64 = 0;
+  size_t i8_b_per_out = 0;
+  uint8_t* LinvI8 = nullptr;  // [p][sets][S][64 x 128 B]  byte slices of alpha_j^2 L_j^{-1} (SWIZZLE_128B tile images)
+  double* cscale = nullptr;   // [p][T64*64]               2^(f_n - 13): row scale of the fixed-point representation
 };
 
 struct Timing {
@@ -74,6 +79,7 @@ struct Ctx {
   int64_t launches = 0;
   cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
   int64_t user_chunk = 0;
+  int var_engine = 0, var_slices = 7;  // BOSIP_B200_VAR_*: which kernel computes ||L^-1 k*||^2
   // chunk workspace (grown on demand)
   size_t ws_bytes = 0;
   char* ws = nullptr;
@@ -151,10 +157,17 @@ int ensure_ws(Ctx* ctx, size_t bytes);
 // fill the likelihood part of the epilogue parameters (gp_p = GP output dimension the likelihood must match)
 int make_like_params(Ctx* ctx, const bosip_b200_like_normal* like, int gp_p, EpiParams* ep);
 // kstar.cu
+// write_k: 0 = mean only, 1 = FP64 K* chunks for vargemm.cu, 2 = byte slices for vargemm_i8.cu (Ks is then the slice buffer)
 int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit,
-                 int nspan, double* Ks, double* mu_part, bool write_k, cudaStream_t st);
+                 int nspan, void* Ks, double* mu_part, int write_k, int slices, cudaStream_t st);
 // vargemm.cu
 int launch_vargemm(Ctx* ctx, const Gp* gp, const double* Ks, int64_t mc, int64_t m_tiles, double* q_part, cudaStream_t st);
+// vargemm_i8.cu
+int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st);
+int i8_nsub(const Gp* gp);
+int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int64_t mc, int64_t m_tiles, double* q_part, double* q,
+                      cudaStream_t st);
+int i8_peak(Ctx* ctx, double* tops);
 // epilogue.cu
 int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* xq, const double* logprior,
                     const double* mean_at_xq, int64_t m_valid, int64_t mc, int nsplit, const double* mu_part,

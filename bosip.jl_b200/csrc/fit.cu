@@ -233,6 +233,7 @@ void gp_destroy(Gp* gp) {
   if (!gp) return;
   cudaFree(gp->Us); cudaFree(gp->scale); cudaFree(gp->As); cudaFree(gp->LinvT);
   cudaFree(gp->L); cudaFree(gp->Linv); cudaFree(gp->a);
+  cudaFree(gp->LinvI8); cudaFree(gp->cscale);
   delete gp;
 }
 

@@ -13,11 +13,22 @@
 namespace bosip {
 
 
-template <int KERNEL, int DP, bool WRITE_K>
+// 4 x 4 byte transpose: out[b] = { byte b of x0, byte b of x1, byte b of x2, byte b of x3 }  (8 PRMT)
+__device__ __forceinline__ void byte_transpose4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t (&o)[4]) {
+  const uint32_t a = __byte_perm(x0, x1, 0x5140), b = __byte_perm(x0, x1, 0x7362);
+  const uint32_t c = __byte_perm(x2, x3, 0x5140), e = __byte_perm(x2, x3, 0x7362);
+  o[0] = __byte_perm(a, c, 0x5410); o[1] = __byte_perm(a, c, 0x7632);
+  o[2] = __byte_perm(b, e, 0x5410); o[3] = __byte_perm(b, e, 0x7632);
+}
+
+// MODE 0: mean only; 1: FP64 K* chunks (vargemm.cu); 2: S unsigned byte slices of round(k * 2^(8S-1)) written as
+// SWIZZLE_128B tile images [j][m-tile][k-block][slice][128 rows][128 B] for the INT8 engine (vargemm_i8.cu)
+template <int KERNEL, int DP, int MODE, int S>
 __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict__ Us, const double* __restrict__ scale,
                                                        const double* __restrict__ As, int Ns, int d,
                                                        const double* __restrict__ xq, long long m_valid, long long mc,
                                                        int nspan, double* __restrict__ Ks, double* __restrict__ mu_part) {
+  constexpr bool WRITE_K = (MODE == 1);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* su = reinterpret_cast<double*>(smem_raw);          // [DP][nspan]
   double* sa = su + (size_t)DP * nspan;                       // [nspan]
@@ -49,6 +60,48 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
 
   double acc = 0.0;
   const int row_sw = (int)(m & 3);
+  if constexpr (MODE == 2) {
+    const double fx = (S == 8) ? 9223372036854775808.0 : (S == 7 ? 36028797018963968.0 : 140737488355328.0);  // 2^(8S-1)
+    const int KB = (Ns + 127) >> 7;
+    unsigned char* tile0 = reinterpret_cast<unsigned char*>(Ks) +
+                           (((size_t)j * (size_t)(mc >> 7) + blockIdx.x) * KB) * (size_t)(S * 16384) + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll 1
+    for (int n = 0; n < len; n += 16) {
+      uint32_t w[S][4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        double r2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          const double2 u01 = *reinterpret_cast<const double2*>(su + (size_t)k * nspan + n + 4 * q4);
+          const double2 u23 = *reinterpret_cast<const double2*>(su + (size_t)k * nspan + n + 4 * q4 + 2);
+          double t0 = uq[k] - u01.x, t1 = uq[k] - u01.y, t2 = uq[k] - u23.x, t3 = uq[k] - u23.y;
+          r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]); r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
+        }
+        double kv[4];
+        unsigned long long iv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2<KERNEL>(r2[e]); iv[e] = __double2ull_rn(kv[e] * fx); }
+        const double2 a01 = *reinterpret_cast<const double2*>(sa + n + 4 * q4);
+        const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 4 * q4 + 2);
+        acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);
+        uint32_t lo[4], hi[4];
+        byte_transpose4((uint32_t)iv[0], (uint32_t)iv[1], (uint32_t)iv[2], (uint32_t)iv[3], lo);
+        byte_transpose4((uint32_t)(iv[0] >> 32), (uint32_t)(iv[1] >> 32), (uint32_t)(iv[2] >> 32), (uint32_t)(iv[3] >> 32), hi);
+#pragma unroll
+        for (int a = 0; a < S; ++a) {  // slice a (0 = most significant) is byte S-1-a
+          const int byte = S - 1 - a;
+          w[a][q4] = byte < 4 ? lo[byte] : hi[byte - 4];
+        }
+      }
+      const int ng = n0 + n;  // global training index of the 16-group
+      unsigned char* dst = tile0 + (size_t)(ng >> 7) * (size_t)(S * 16384) + (((((ng & 127) >> 4) ^ tid) & 7) << 4);
+#pragma unroll
+      for (int a = 0; a < S; ++a) *reinterpret_cast<uint4*>(dst + (size_t)a * 16384) = make_uint4(w[a][0], w[a][1], w[a][2], w[a][3]);
+    }
+    mu_part[((size_t)split * p + j) * mc + m] = acc;
+    return;
+  }
 #pragma unroll 1
   for (int n = 0; n < len; n += 4) {
     double r2[4] = {0.0, 0.0, 0.0, 0.0};
@@ -77,29 +130,36 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
   mu_part[((size_t)split * p + j) * mc + m] = acc;
 }
 
-template <int KERNEL, int DP>
-static int launch_kd(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
-                     double* Ks, double* mu_part, bool write_k, cudaStream_t st) {
+template <int KERNEL, int DP, int MODE, int S>
+static int launch_kds(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
+                      void* Ks, double* mu_part, cudaStream_t st) {
   dim3 grid((unsigned)m_tiles, (unsigned)nsplit, (unsigned)gp->p);
   size_t smem = (size_t)(DP + 1) * nspan * sizeof(double);
-  if (write_k) {
-    auto kern = kstar_kernel<KERNEL, DP, true>;
-    BOSIP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TILE_M, smem, st>>>(gp->Us, gp->scale, gp->As, gp->Ns, gp->d, xq, m_valid, mc, nspan, Ks, mu_part);
-  } else {
-    auto kern = kstar_kernel<KERNEL, DP, false>;
-    BOSIP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TILE_M, smem, st>>>(gp->Us, gp->scale, gp->As, gp->Ns, gp->d, xq, m_valid, mc, nspan, Ks, mu_part);
-  }
+  auto kern = kstar_kernel<KERNEL, DP, MODE, S>;
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, TILE_M, smem, st>>>(gp->Us, gp->scale, gp->As, gp->Ns, gp->d, xq, m_valid, mc, nspan, reinterpret_cast<double*>(Ks), mu_part);
   BOSIP_CUDA(ctx, cudaGetLastError());
   return 0;
 }
 
+template <int KERNEL, int DP>
+static int launch_kd(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
+                     void* Ks, double* mu_part, int write_k, int slices, cudaStream_t st) {
+  if (write_k == 0) return launch_kds<KERNEL, DP, 0, 0>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, st);
+  if (write_k == 1) return launch_kds<KERNEL, DP, 1, 0>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, st);
+  switch (slices) {
+    case 6: return launch_kds<KERNEL, DP, 2, 6>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, st);
+    case 7: return launch_kds<KERNEL, DP, 2, 7>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, st);
+    case 8: return launch_kds<KERNEL, DP, 2, 8>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, st);
+  }
+  BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unsupported slice count");
+}
+
 template <int KERNEL>
 static int launch_k(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
-                    double* Ks, double* mu_part, bool write_k, cudaStream_t st) {
+                    void* Ks, double* mu_part, int write_k, int slices, cudaStream_t st) {
 #define BOSIP_DP_CASE(DPV) \
-  case DPV: return launch_kd<KERNEL, DPV>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
+  case DPV: return launch_kd<KERNEL, DPV>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
   switch (gp->dp) {
     BOSIP_DP_CASE(2) BOSIP_DP_CASE(3) BOSIP_DP_CASE(4) BOSIP_DP_CASE(5) BOSIP_DP_CASE(6) BOSIP_DP_CASE(8)
     BOSIP_DP_CASE(10) BOSIP_DP_CASE(12) BOSIP_DP_CASE(16) BOSIP_DP_CASE(24) BOSIP_DP_CASE(32)
@@ -109,11 +169,11 @@ static int launch_k(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, i
 }
 
 int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
-                 double* Ks, double* mu_part, bool write_k, cudaStream_t st) {
+                 void* Ks, double* mu_part, int write_k, int slices, cudaStream_t st) {
   switch (gp->kernel_id) {
-    case BOSIP_B200_KERNEL_SE: return launch_k<BOSIP_B200_KERNEL_SE>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
-    case BOSIP_B200_KERNEL_MATERN32: return launch_k<BOSIP_B200_KERNEL_MATERN32>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
-    case BOSIP_B200_KERNEL_MATERN52: return launch_k<BOSIP_B200_KERNEL_MATERN52>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, st);
+    case BOSIP_B200_KERNEL_SE: return launch_k<BOSIP_B200_KERNEL_SE>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
+    case BOSIP_B200_KERNEL_MATERN32: return launch_k<BOSIP_B200_KERNEL_MATERN32>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
+    case BOSIP_B200_KERNEL_MATERN52: return launch_k<BOSIP_B200_KERNEL_MATERN52>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
   }
   BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown kernel id");
 }

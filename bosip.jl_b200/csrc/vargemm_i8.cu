@@ -1,0 +1,453 @@
+// Variance contraction q = ||alpha^2 L^{-1} k*||^2 on the INT8 tcgen05 tensor cores (UTCIMMA, accumulators in TMEM):
+// the second engine behind BOSS.var / mean_and_var (call sites /root/reference/src/likelihoods/normal.jl:37,43,60,68).
+//
+// Error-free splitting (Ozaki scheme, base 256).  Both operands are written as fixed-point integers
+//     k(x_i, X_k)             = IA[i,k] * 2^-(8S-1),        IA in [0, 2^(8S-1)]   (kernel values lie in [0, 1])
+//     alpha^2 Linv[n,k]       = IB[n,k] * 2^(f_n-(8S-2)),   |IB| <= 2^(8S-2)      (f_n: per-row power-of-two scale)
+// and cut into S byte slices (A unsigned, B balanced signed).  A slice product A_a . B_b^T is an exact int32 GEMM; all pairs
+// with a + b = g share the weight 2^-8g and accumulate in ONE TMEM accumulator.  Pairs with a + b >= S are below the kept
+// precision (2^-8S relative to the row scale) and are skipped, which leaves S(S+1)/2 INT8 GEMMs.  The FP64 value
+//     v[i,n] = 2^(f_n-13) * sum_g 2^-8g D_g[i,n]
+// is assembled in the epilogue (Horner, exact int->double conversions), squared and added to the row sum.
+//
+// Shape of one CTA step: query tile 128 rows (MMA M) x 64 rows of L^{-1} (n-tile) x one 128-byte k-block.  All S group
+// accumulators of the n-tile are live at once (S x 64 TMEM columns <= 512), so every operand tile is loaded exactly once per
+// (n-tile, k-block).  For slice a of the query tile the B operands it meets are the slices b = 0..S-1-a; they are stored
+// contiguously in descending b, so up to four of them form ONE tcgen05.mma of N = 256 whose output columns are four
+// adjacent group accumulators.  Roles: warp 0 = TMA producer (cp.async.bulk, full/empty mbarriers), warp 1 = TMEM allocation
+// + the single MMA-issuing thread, warps 2..9 = epilogue (tcgen05.ld, FP64 assembly, row sums).
+#include "common.cuh"
+
+namespace bosip {
+
+constexpr int I8_BM = 128, I8_BN = 64, I8_BK = 128;
+constexpr int I8_A_TILE = I8_BM * I8_BK;  // 16 KB: [128 rows][128 B], SWIZZLE_128B image
+constexpr int I8_B_TILE = I8_BN * I8_BK;  //  8 KB: [ 64 rows][128 B], SWIZZLE_128B image
+constexpr int I8_THREADS = 320;
+constexpr int I8_EPI_WARPS = 8;
+
+template <int S> struct I8Cfg {
+  static constexpr int A_SLOTS = (S >= 8) ? 5 : 6;
+  static constexpr int B_SET = S * I8_B_TILE;
+  static constexpr size_t SMEM = 1024 + (size_t)A_SLOTS * I8_A_TILE + 2 * (size_t)B_SET + 256;
+};
+
+// byte offset of (row r, k-byte c) inside a SWIZZLE_128B K-major tile image: 16-byte chunk (c >> 4) is stored at chunk ^ (r & 7)
+__host__ __device__ __forceinline__ uint32_t sw128(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 4) ^ r) & 7) << 4) + (c & 15));
+}
+// number of (n-tile, k-block) operand sets stored before 64-row tile t: tile u owns (u >> 1) + 1 k-blocks (lower triangle)
+__host__ __device__ __forceinline__ int i8_tile_off(int t) { const int v = t >> 1; return (t & 1) ? (v + 1) * (v + 1) : v * (v + 1); }
+// n-tiles are dealt to the `nsub` work items of a (output, query tile) in zig-zag order from the last (most expensive) tile
+__host__ __device__ __forceinline__ int i8_subset(int t, int T64, int nsub) {
+  const int r = (T64 - 1 - t) % (2 * nsub);
+  return r < nsub ? r : 2 * nsub - 1 - r;
+}
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol error traps (-> cudaErrorLaunchFailure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {  // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_u8s8(int M, int N) {  // D = s32, A = u8, B = s8, both K-major
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ double i32_to_f64(uint32_t v) {  // exact: 2^52 + 2^31 + v as a bit pattern, minus the offset
+  return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM
+struct I8Args {
+  const uint8_t* A;       // [p][mtA][KB][S][16 KB]     K* slices (kstar.cu, i8 mode)
+  const uint8_t* B;       // [p][sets][S][8 KB]         alpha^2 L^{-1} slices, position = byte significance (descending b)
+  const double* cs;       // [p][T64*64]                2^(f_n - 13), 0 for padding rows
+  double* q_part;         // [nsub][p][mc]
+  long long mc;
+  size_t b_per_out;       // bytes of B per output
+  int KB, T64, mtA, m_tiles, p, nsub, n_items;
+};
+
+template <int S>
+__global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args g) {
+  using Cfg = I8Cfg<S>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;
+  unsigned char* sB = base + (size_t)Cfg::A_SLOTS * I8_A_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * (size_t)Cfg::B_SET);
+  uint64_t* a_full = bars;                       // [A_SLOTS]
+  uint64_t* a_empty = bars + Cfg::A_SLOTS;       // [A_SLOTS]
+  uint64_t* b_full = bars + 2 * Cfg::A_SLOTS;    // [2]
+  uint64_t* b_empty = b_full + 2;                // [2]
+  uint64_t* t_full = b_empty + 2;                // accumulators complete -> epilogue
+  uint64_t* t_empty = t_full + 1;                // accumulators drained  -> MMA
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double half_sum[I8_BM];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, I8_EPI_WARPS);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      uint32_t a_cnt = 0, b_cnt = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int sub = item % g.nsub, grp = item / g.nsub, mt = grp % g.m_tiles, j = grp / g.m_tiles;
+        const uint8_t* Aj = g.A + ((size_t)j * g.mtA + mt) * g.KB * S * I8_A_TILE;
+        const uint8_t* Bj = g.B + (size_t)j * g.b_per_out;
+        for (int t = g.T64 - 1; t >= 0; --t) {
+          if (i8_subset(t, g.T64, g.nsub) != sub) continue;
+          const int nkb = (t >> 1) + 1;
+          const uint8_t* Bt = Bj + (size_t)i8_tile_off(t) * Cfg::B_SET;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t bs = b_cnt & 1;
+            mbar_wait_b(&b_empty[bs], ((b_cnt >> 1) & 1) ^ 1);
+            mbar_expect_tx(&b_full[bs], Cfg::B_SET);
+            bulk_g2s(sB + (size_t)bs * Cfg::B_SET, Bt + (size_t)kb * Cfg::B_SET, Cfg::B_SET, &b_full[bs]);
+            ++b_cnt;
+            const uint8_t* Ak = Aj + (size_t)kb * S * I8_A_TILE;
+#pragma unroll 1
+            for (int a = 0; a < S; ++a) {
+              const uint32_t as = a_cnt % Cfg::A_SLOTS;
+              mbar_wait_b(&a_empty[as], ((a_cnt / Cfg::A_SLOTS) & 1) ^ 1);
+              mbar_expect_tx(&a_full[as], I8_A_TILE);
+              bulk_g2s(sA + (size_t)as * I8_A_TILE, Ak + (size_t)a * I8_A_TILE, I8_A_TILE, &a_full[as]);
+              ++a_cnt;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t a_cnt = 0, b_cnt = 0, tile_cnt = 0;
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int sub = item % g.nsub;
+        for (int t = g.T64 - 1; t >= 0; --t) {
+          if (i8_subset(t, g.T64, g.nsub) != sub) continue;
+          const int nkb = (t >> 1) + 1;
+          mbar_wait_b(t_empty, (tile_cnt & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t bs = b_cnt & 1;
+            mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1);
+            const uint32_t b_addr = sB_u + bs * (uint32_t)Cfg::B_SET;
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              const uint32_t as = a_cnt % Cfg::A_SLOTS;
+              mbar_wait_b(&a_full[as], (a_cnt / Cfg::A_SLOTS) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+              const uint32_t a_addr = sA_u + as * (uint32_t)I8_A_TILE;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t da = umma_desc_sw128(a_addr + ks * 32);
+#pragma unroll
+                for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> groups' columns 64 (c0 - a) ..
+                  const int nb = (S - c0) < 4 ? (S - c0) : 4;
+                  const uint64_t db = umma_desc_sw128(b_addr + (uint32_t)c0 * I8_B_TILE + ks * 32);
+                  umma_i8(tmem + (uint32_t)(64 * (c0 - a)), da, db, umma_idesc_u8s8(I8_BM, 64 * nb), (kb | ks | a) ? 1u : 0u);
+                }
+              }
+              umma_commit(&a_empty[as]);
+              ++a_cnt;
+            }
+            umma_commit(&b_empty[bs]);
+            ++b_cnt;
+          }
+          umma_commit(t_full);
+          ++tile_cnt;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue: 8 warps, thread = (row, 32-column half)
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lanes 32 quad .. 32 quad + 31 are the ones this warp may read
+    const int half = ew >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * half);
+    uint32_t tile_cnt = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+      const int sub = item % g.nsub, grp = item / g.nsub, mt = grp % g.m_tiles, j = grp / g.m_tiles;
+      const double* csj = g.cs + (size_t)j * g.T64 * I8_BN;
+      double rs = 0.0;
+      for (int t = g.T64 - 1; t >= 0; --t) {
+        if (i8_subset(t, g.T64, g.nsub) != sub) continue;
+        mbar_wait_b(t_full, tile_cnt & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        double w[32];
+        uint32_t v[32];
+        // Horner from the least significant group: group gi lives at columns 64 (S-1-gi)
+        tmem_ld32(taddr, v);  // gi = S-1
+#pragma unroll
+        for (int c = 0; c < 32; ++c) w[c] = i32_to_f64(v[c]);
+#pragma unroll
+        for (int gi = S - 2; gi >= 0; --gi) {
+          tmem_ld32(taddr + (uint32_t)(64 * (S - 1 - gi)), v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) w[c] = fma(w[c], 0.00390625, i32_to_f64(v[c]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty);
+        ++tile_cnt;
+        const double* cst = csj + (size_t)t * I8_BN + 32 * half;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const double x = w[c] * __ldg(cst + c);
+          rs = fma(x, x, rs);
+        }
+      }
+      // combine the two column halves of a row in a fixed order, one partial per work item
+      if (half == 1) half_sum[row] = rs;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (half == 0) g.q_part[((size_t)sub * g.p + j) * g.mc + (size_t)mt * I8_BM + row] = rs + half_sum[row];
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(512));
+}
+
+__global__ void i8_qsum_kernel(const double* __restrict__ part, int nsub, size_t n, double* __restrict__ q) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = part[i];
+  for (int u = 1; u < nsub; ++u) s += part[(size_t)u * n + i];
+  q[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ slicing L^{-1} (once per fit)
+// f_n = smallest exponent with max_k |alpha^2 Linv[n,k]| <= 2^f_n
+__global__ void i8_rowscale_kernel(const double* __restrict__ Linv, const double* __restrict__ alpha2, int N, int NP, int* __restrict__ fexp,
+                                   double* __restrict__ cs) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (n >= NP) return;
+  if (n >= N) { fexp[(size_t)j * NP + n] = 0; cs[(size_t)j * NP + n] = 0.0; return; }
+  const double* Lj = Linv + (size_t)j * N * N;
+  double mx = 0.0;
+  for (int k = 0; k <= n; ++k) mx = fmax(mx, fabs(Lj[(size_t)n + (size_t)k * N]));
+  mx *= alpha2[j];
+  int e = 0;
+  if (mx > 0.0) { frexp(mx, &e); if (ldexp(1.0, e - 1) == mx) e -= 1; }  // mx = m 2^e, m in [0.5, 1); exact powers of two fit one lower
+  fexp[(size_t)j * NP + n] = e;
+  cs[(size_t)j * NP + n] = ldexp(1.0, e - 13);
+}
+
+// thread = (set, row, 16-byte chunk): writes the S slice bytes of 16 consecutive k
+template <int S>
+__global__ void i8_slice_linv_kernel(const double* __restrict__ Linv, const double* __restrict__ alpha2, const int* __restrict__ fexp,
+                                     int N, int NP, int T64, size_t b_per_out, uint8_t* __restrict__ B) {
+  const int j = blockIdx.y;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = (int)(e & 7), r = (int)((e >> 3) & 63);
+  const size_t set = e >> 9;
+  const int sets = i8_tile_off(T64);
+  if (set >= (size_t)sets) return;
+  // invert the triangular set index: tile t owns sets [off(t), off(t) + (t >> 1) + 1)
+  int t = 0;
+  while (t + 1 < T64 && (size_t)i8_tile_off(t + 1) <= set) ++t;
+  const int kb = (int)(set - i8_tile_off(t));
+  const int n = t * I8_BN + r;
+  const double* Lj = Linv + (size_t)j * N * N;
+  const int f = (n < N) ? fexp[(size_t)j * NP + n] : 0;
+  unsigned long long bias = 0;
+#pragma unroll
+  for (int b = 0; b < S - 1; ++b) bias |= 0x80ull << (8 * b);
+  uint32_t out[S][4];
+#pragma unroll
+  for (int s = 0; s < S; ++s) { out[s][0] = out[s][1] = out[s][2] = out[s][3] = 0u; }
+  for (int i = 0; i < 16; ++i) {
+    const int k = kb * I8_BK + chunk * 16 + i;
+    long long I = 0;
+    if (n < N && k <= n) {
+      const double v = alpha2[j] * Lj[(size_t)n + (size_t)k * N];
+      I = __double2ll_rn(ldexp(v, 8 * S - 2 - f));
+    }
+    const unsigned long long u = (unsigned long long)I + bias;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      uint32_t byte = (uint32_t)(u >> (8 * s)) & 0xFFu;
+      if (s < S - 1) byte ^= 0x80u;  // balanced digit in [-128, 127]; the top byte is signed as it stands
+      out[s][i >> 2] |= byte << (8 * (i & 3));
+    }
+  }
+  uint8_t* dst = B + (size_t)j * b_per_out + set * (size_t)(S * I8_B_TILE) + sw128(r, chunk * 16);
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+    *reinterpret_cast<uint4*>(dst + (size_t)s * I8_B_TILE) = make_uint4(out[s][0], out[s][1], out[s][2], out[s][3]);
+}
+
+int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
+  if (gp->i8_S == S && gp->LinvI8) return 0;
+  if (S < 6 || S > 8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: slices must be 6, 7 or 8");
+  // int32 accumulator bound: up to S pairs per group, each |sum| <= K * 255 * 128
+  if ((double)gp->N * S * 255.0 * 128.0 >= 2147483647.0)
+    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: N too large for exact int32 accumulation");
+  if (gp->LinvI8) { cudaFree(gp->LinvI8); gp->LinvI8 = nullptr; }
+  if (gp->cscale) { cudaFree(gp->cscale); gp->cscale = nullptr; }
+  const int N = gp->N, p = gp->p;
+  const int T64 = (N + I8_BN - 1) / I8_BN, NP = T64 * I8_BN;
+  const size_t sets = (size_t)i8_tile_off(T64);
+  const size_t b_per_out = sets * S * I8_B_TILE;
+  int* fexp = nullptr; double* dAlpha2 = nullptr;
+  BOSIP_CUDA(ctx, cudaMalloc(&gp->LinvI8, b_per_out * p));
+  BOSIP_CUDA(ctx, cudaMalloc(&gp->cscale, (size_t)p * NP * 8));
+  BOSIP_CUDA(ctx, cudaMalloc(&fexp, (size_t)p * NP * 4));
+  BOSIP_CUDA(ctx, cudaMalloc(&dAlpha2, (size_t)p * 8));
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(dAlpha2, gp->alpha2, (size_t)p * 8, cudaMemcpyHostToDevice, st));
+  i8_rowscale_kernel<<<dim3((NP + 127) / 128, p), 128, 0, st>>>(gp->Linv, dAlpha2, N, NP, fexp, gp->cscale);
+  const size_t threads = sets * 64 * 8;
+  const dim3 grid((unsigned)((threads + 255) / 256), (unsigned)p);
+  switch (S) {
+    case 6: i8_slice_linv_kernel<6><<<grid, 256, 0, st>>>(gp->Linv, dAlpha2, fexp, N, NP, T64, b_per_out, gp->LinvI8); break;
+    case 7: i8_slice_linv_kernel<7><<<grid, 256, 0, st>>>(gp->Linv, dAlpha2, fexp, N, NP, T64, b_per_out, gp->LinvI8); break;
+    default: i8_slice_linv_kernel<8><<<grid, 256, 0, st>>>(gp->Linv, dAlpha2, fexp, N, NP, T64, b_per_out, gp->LinvI8); break;
+  }
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  cudaFree(fexp); cudaFree(dAlpha2);
+  gp->i8_S = S; gp->i8_T64 = T64; gp->i8_b_per_out = b_per_out;
+  return 0;
+}
+
+int i8_nsub(const Gp* gp) {
+  const int T64 = (gp->N + I8_BN - 1) / I8_BN;
+  int nsub = T64 / 4;
+  return nsub < 1 ? 1 : (nsub > 8 ? 8 : nsub);
+}
+
+template <int S>
+static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
+  const int grid = a.n_items < ctx->sms ? a.n_items : ctx->sms;
+  vargemm_i8_kernel<S><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// Ks8: [p][mc/128][KB][S][16 KB]; q_part: [nsub][p][mc] scratch; q: [p][mc]
+int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int64_t mc, int64_t m_tiles, double* q_part, double* q, cudaStream_t st) {
+  I8Args a;
+  a.A = Ks8; a.B = gp->LinvI8; a.cs = gp->cscale; a.q_part = q_part; a.mc = mc; a.b_per_out = gp->i8_b_per_out;
+  a.KB = (gp->N + I8_BK - 1) / I8_BK; a.T64 = gp->i8_T64; a.mtA = (int)(mc / I8_BM); a.m_tiles = (int)m_tiles; a.p = gp->p;
+  a.nsub = i8_nsub(gp); a.n_items = (int)(m_tiles * gp->p * a.nsub);
+  switch (gp->i8_S) {
+    case 6: BOSIP_TRY(launch_i8<6>(ctx, a, st)); break;
+    case 7: BOSIP_TRY(launch_i8<7>(ctx, a, st)); break;
+    case 8: BOSIP_TRY(launch_i8<8>(ctx, a, st)); break;
+    default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine not prepared");
+  }
+  const size_t n = (size_t)gp->p * mc;
+  i8_qsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q_part, a.nsub, n, q);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ INT8 roofline probe
+// One CTA per SM issues `iters` x 4 tcgen05.mma (M=128, N=256, K=32) on operands that stay resident in shared memory.
+__global__ void __launch_bounds__(128) i8_peak_kernel(int iters) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sA = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = sA + 4 * I8_A_TILE;
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (4 * I8_A_TILE + 4 * 256 * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (tid == 0) { mbar_init(&done, 1); mbar_fence_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base_s;
+  if (tid == 0) {
+    for (int it = 0; it < iters; ++it) {
+      const int st = it & 3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_i8(tb + (uint32_t)((it & 1) * 256), umma_desc_sw128(smem_u32(sA + st * I8_A_TILE) + k * 32),
+                umma_desc_sw128(smem_u32(sB + st * 256 * 128) + k * 32), umma_idesc_u8s8(128, 256), 1u);
+    }
+    umma_commit(&done);
+    mbar_wait_b(&done, 0);
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
+}
+
+int i8_peak(Ctx* ctx, double* tops) {
+  const size_t smem = 4 * (size_t)I8_A_TILE + 4 * 256 * 128 + 1024;
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = ctx->s_comp;
+  const int iters = 10000;
+  i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(200);
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_t0, st));
+    i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(iters);
+    BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_t1, st));
+    BOSIP_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    float ms = 0;
+    BOSIP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+    if (ms < best) best = ms;
+  }
+  *tops = 2.0 * (double)ctx->sms * iters * 4.0 * 128.0 * 256.0 * 32.0 / (best * 1e-3) / 1e12;
+  return 0;
+}
+
+}  // namespace bosip

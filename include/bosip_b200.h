@@ -132,6 +132,19 @@ int bosip_b200_set_stream(bosip_b200_ctx* ctx, void* cuda_stream);
 int bosip_b200_launch_count(bosip_b200_ctx* ctx, int64_t* out);
 /* Upper bound for the number of query points processed per internal chunk (0 = library default). */
 int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
+/* Which kernel evaluates the variance contraction ||alpha^2 L^-1 k*||^2 of BOSS.var / mean_and_var
+ * (src/likelihoods/normal.jl:37,43,60,68):
+ *   BOSIP_B200_VAR_FP64  mma.sync FP64 tensor cores (DMMA), plain Float64 arithmetic;
+ *   BOSIP_B200_VAR_INT8  tcgen05 INT8 tensor cores on error-free byte slices of both operands (Ozaki splitting):
+ *                        `slices` bytes of fixed point per operand (6, 7 or 8; 0 = 7, i.e. 2^-56 of the row scale),
+ *                        integer products exact, one FP64 rounding per Horner step in the epilogue.
+ * Both satisfy the 1e-10 parity bound; results differ in the last bits. */
+#define BOSIP_B200_VAR_FP64 0
+#define BOSIP_B200_VAR_INT8 1
+int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
+/* Measured issue-rate ceiling of tcgen05.mma kind::i8 (M=128, N=256, operands resident in shared memory) on all SMs,
+ * in TOPS counting 2 ops per multiply-accumulate: the roofline denominator of the INT8 engine. */
+int bosip_b200_int8_peak(bosip_b200_ctx* ctx, double* tops);
 
 /* ---- GP conditioning: replaces BOSS.model_posterior(bosip.problem)
  *      (src/posterior/log_posterior.jl:81,115,148,182,214) --------------------------------------------- */

@@ -1,0 +1,204 @@
+// Dev probe for the INT8 tcgen05 path (sm_100a): (1) correctness of the shared-memory/instruction descriptors for
+// K-major SWIZZLE_128B int8 operands against a host reference, (2) issue-rate ceiling of tcgen05.mma.kind::i8 for
+// N = 128 / 256 with cta_group::1.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/i8mma_probe tools/i8mma_probe.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 2000000000ll) { printf("TIMEOUT tag %d block %d thread %d\n", tag, blockIdx.x, threadIdx.x); asm volatile("trap;"); }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {  // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// image of a [rows][128 B] K-major tile in the SWIZZLE_128B layout: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+__host__ __device__ inline size_t sw128(int r, int kbyte) { return (size_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((kbyte >> 4) ^ (r & 7)) & 7) << 4) + (kbyte & 15); }
+
+// ---------------------------------------------------------------- check kernel: D[128][N] = A[128][K] * B[N][K]^T, K = KB * 128
+template <int N>
+__global__ void __launch_bounds__(128) check_kernel(const int8_t* __restrict__ Aimg, const int8_t* __restrict__ Bimg, int KB, int32_t* __restrict__ D) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full, done;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  unsigned char* sA = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = sA + (size_t)KB * 16384;
+  if (tid == 0) { mbar_init(&full, 1); mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    mbar_expect_tx(&full, (uint32_t)KB * (16384 + N * 128));
+    for (int kb = 0; kb < KB; ++kb) {
+      bulk_g2s(sA + (size_t)kb * 16384, Aimg + (size_t)kb * 16384, 16384, &full);
+      bulk_g2s(sB + (size_t)kb * N * 128, Bimg + (size_t)kb * N * 128, N * 128, &full);
+    }
+    mbar_wait(&full, 0, 1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t idesc = make_idesc(128, N);
+    for (int kb = 0; kb < KB; ++kb)
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = make_desc(smem_u32(sA + (size_t)kb * 16384) + k * 32);
+        const uint64_t db = make_desc(smem_u32(sB + (size_t)kb * N * 128) + k * 32);
+        mma_i8(tb, da, db, idesc, (kb | k) ? 1u : 0u);
+      }
+    mma_commit(&done);
+  }
+  __syncthreads();
+  mbar_wait(&done, 0, 2);
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + c0, v);
+    for (int i = 0; i < 32; ++i) D[(size_t)tid * N + c0 + i] = (int32_t)v[i];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
+}
+
+// ---------------------------------------------------------------- peak kernel: issue `iters` x 4 MMAs on resident operands
+template <int N>
+__global__ void __launch_bounds__(128) peak_kernel(int iters, int nacc) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  unsigned char* sA = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = sA + 4 * 16384;
+  for (int i = tid; i < (4 * 16384 + 4 * N * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (tid == 0) { mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N);
+    for (int it = 0; it < iters; ++it) {
+      const int st = it & 3;
+      const uint32_t d = tb + (uint32_t)((it % nacc) * N);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        mma_i8(d, make_desc(smem_u32(sA + st * 16384) + k * 32), make_desc(smem_u32(sB + st * N * 128) + k * 32), idesc, 1u);
+    }
+    mma_commit(&done);
+    mbar_wait(&done, 0, 3);
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
+}
+
+template <int N>
+static int run_check(int KB) {
+  const int K = KB * 128;
+  std::vector<int8_t> A((size_t)128 * K), B((size_t)N * K), Aimg((size_t)KB * 16384), Bimg((size_t)KB * N * 128);
+  srand(1234 + N + KB);
+  for (auto& x : A) x = (int8_t)(rand() % 129 - 64);
+  for (auto& x : B) x = (int8_t)(rand() % 129 - 64);
+  for (int r = 0; r < 128; ++r) for (int k = 0; k < K; ++k) Aimg[(size_t)(k >> 7) * 16384 + sw128(r, k & 127)] = A[(size_t)r * K + k];
+  for (int r = 0; r < N; ++r) for (int k = 0; k < K; ++k) Bimg[(size_t)(k >> 7) * N * 128 + sw128(r, k & 127)] = B[(size_t)r * K + k];
+  int8_t *dA, *dB; int32_t* dD;
+  CK(cudaMalloc(&dA, Aimg.size())); CK(cudaMalloc(&dB, Bimg.size())); CK(cudaMalloc(&dD, (size_t)128 * N * 4));
+  CK(cudaMemcpy(dA, Aimg.data(), Aimg.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, Bimg.data(), Bimg.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, (size_t)128 * N * 4));
+  const size_t smem = (size_t)KB * (16384 + N * 128) + 1024;
+  CK(cudaFuncSetAttribute(check_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  check_kernel<N><<<1, 128, smem>>>(dA, dB, KB, dD);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> D((size_t)128 * N);
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  long long bad = 0; int first = -1;
+  for (int r = 0; r < 128; ++r) for (int c = 0; c < N; ++c) {
+    int32_t ref = 0;
+    for (int k = 0; k < K; ++k) ref += (int32_t)A[(size_t)r * K + k] * (int32_t)B[(size_t)c * K + k];
+    if (ref != D[(size_t)r * N + c]) { if (first < 0) first = r * N + c; ++bad; }
+  }
+  printf("check N=%d K=%d: %lld mismatches of %d%s\n", N, K, bad, 128 * N, bad ? " (FAIL)" : " (exact)");
+  if (bad) printf("  first mismatch at row %d col %d: got %d\n", first / N, first % N, D[first]);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return bad ? 1 : 0;
+}
+
+template <int N>
+static void run_peak(int blocks, int iters, int nacc) {
+  const size_t smem = 4 * 16384 + 4 * (size_t)N * 128 + 1024;
+  CK(cudaFuncSetAttribute(peak_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  peak_kernel<N><<<blocks, 128, smem>>>(100, nacc);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(a));
+    peak_kernel<N><<<blocks, 128, smem>>>(iters, nacc);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+  }
+  const double macs = (double)blocks * iters * 4.0 * 128.0 * N * 32.0;
+  printf("peak N=%d blocks=%d iters=%d nacc=%d: %.3f ms  %.1f TOPS (2*MAC)  %.0f MAC/clk/SM @1.965GHz\n", N, blocks, iters, nacc, best,
+         2.0 * macs / (best * 1e-3) / 1e12, macs / blocks / (best * 1e-3) / 1.965e9);
+}
+
+int main(int argc, char** argv) {
+  int rc = 0;
+  rc |= run_check<128>(1);
+  rc |= run_check<128>(3);
+  rc |= run_check<256>(2);
+  rc |= run_check<64>(2);
+  if (rc) { printf("descriptor check FAILED; skipping peak\n"); return 1; }
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  run_peak<128>(1, 20000, 1);
+  run_peak<128>(1, 20000, 4);
+  run_peak<256>(1, 10000, 2);
+  run_peak<128>(sms, 20000, 4);
+  run_peak<256>(sms, 10000, 2);
+  run_peak<64>(sms, 20000, 4);
+  return 0;
+}
