@@ -1,6 +1,7 @@
 // C ABI of libbosip_b200.so (include/bosip_b200.h): context lifecycle, the chunked evaluation pipeline
 // (H2D staging | cross-kernel+mean | variance GEMM | fused epilogue | reductions | D2H), and the entry points.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -189,13 +190,6 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   const bool host = (sw.mem == BOSIP_B200_HOST);
   const bool gen = (sw.xq == nullptr);
 
-  // ---- n-split of the cross-kernel so that its shared-memory footprint allows >= 4 CTAs per SM
-  int nspan = (int)((56 * 1024) / (8 * (gp->dp + 1))) & ~15;
-  nspan = std::max(16, std::min(nspan, Ns));
-  int nsplit = (Ns + nspan - 1) / nspan;
-  nspan = (int)round_up((Ns + nsplit - 1) / nsplit, 16);
-  nsplit = (Ns + nspan - 1) / nspan;
-
   // ---- variance engine (FP64 DMMA or INT8 tcgen05 with error-free slicing)
   const bool i8 = sw.need_var && ctx->var_engine == BOSIP_B200_VAR_INT8;
   const int S8 = ctx->var_slices, KB8 = (gp->N + 127) / 128;
@@ -204,6 +198,16 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     for (Gp* gf : sw.fits) BOSIP_TRY(i8_prepare(ctx, gf, S8, ctx->s_comp));
     nsub8 = i8_nsub(gp);
   }
+
+  // ---- n-split of the cross-kernel so that its shared-memory footprint allows >= 4 CTAs per SM
+  // (the INT8 slice writer walks 32 training points per iteration: spans are multiples of 32 there)
+  static const int kstar_smem_kb = getenv("BOSIP_KSTAR_SMEM_KB") ? atoi(getenv("BOSIP_KSTAR_SMEM_KB")) : 56;  // dev A/B switch
+  const int span_q = i8 ? 32 : 16;
+  int nspan = (int)((kstar_smem_kb * 1024) / (8 * (gp->dp + 1))) & ~(span_q - 1);
+  nspan = std::max(span_q, std::min(nspan, (int)round_up(Ns, span_q)));
+  int nsplit = (Ns + nspan - 1) / nspan;
+  nspan = (int)round_up((Ns + nsplit - 1) / nsplit, span_q);
+  nsplit = (Ns + nspan - 1) / nspan;
 
   // ---- chunk size
   int64_t mc;

@@ -55,6 +55,14 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
 #pragma unroll
   for (int k = 0; k < DP; ++k) uq[k] = (k < d) ? xq[m_src * d + k] * scale[j * DP + k] : 0.0;
 
+  if constexpr (MODE == 2) {  // the 32-wide loop may read up to 16 entries past `len`: give them finite values and zero weights
+    if (len & 31) {
+      for (int e = tid; e < 16 * (DP + 1); e += TILE_M) {
+        const int k = e >> 4, i = len + (e & 15);
+        if (k < DP) su[(size_t)k * nspan + i] = 0.0; else sa[i] = 0.0;
+      }
+    }
+  }
   __syncthreads();  // barrier init visible to all waiters
   mbar_wait(&bar, 0);
 
@@ -65,11 +73,14 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
     const int KB = (Ns + 127) >> 7;
     unsigned char* tile0 = reinterpret_cast<unsigned char*>(Ks) +
                            (((size_t)j * (size_t)(mc >> 7) + blockIdx.x) * KB) * (size_t)(S * 16384) + (tid >> 3) * 1024 + (tid & 7) * 128;
+    // 32 training points per iteration: the two 16-byte chunks of a slice form one aligned 32-byte sector of the swizzled row
+    const int len32 = (len + 31) & ~31;
+    const int odd = tid & 1;  // chunk c sits at c ^ (row & 7): for odd rows the two halves of a sector swap places
 #pragma unroll 1
-    for (int n = 0; n < len; n += 16) {
-      uint32_t w[S][4];
+    for (int n = 0; n < len32; n += 32) {
+      uint32_t w[S][8];
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
+      for (int q4 = 0; q4 < 8; ++q4) {
         double r2[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
@@ -94,10 +105,15 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
           w[a][q4] = byte < 4 ? lo[byte] : hi[byte - 4];
         }
       }
-      const int ng = n0 + n;  // global training index of the 16-group
-      unsigned char* dst = tile0 + (size_t)(ng >> 7) * (size_t)(S * 16384) + (((((ng & 127) >> 4) ^ tid) & 7) << 4);
+      const int ng = n0 + n;  // global training index of the 32-group (n0 is a multiple of 32 in this mode)
+      unsigned char* dst = tile0 + (size_t)(ng >> 7) * (size_t)(S * 16384) + ((((((ng & 127) >> 4) ^ tid) & 7) & ~1) << 4);
 #pragma unroll
-      for (int a = 0; a < S; ++a) *reinterpret_cast<uint4*>(dst + (size_t)a * 16384) = make_uint4(w[a][0], w[a][1], w[a][2], w[a][3]);
+      for (int a = 0; a < S; ++a) {
+        const uint32_t x0 = odd ? w[a][4] : w[a][0], x1 = odd ? w[a][5] : w[a][1], x2 = odd ? w[a][6] : w[a][2], x3 = odd ? w[a][7] : w[a][3];
+        const uint32_t x4 = odd ? w[a][0] : w[a][4], x5 = odd ? w[a][1] : w[a][5], x6 = odd ? w[a][2] : w[a][6], x7 = odd ? w[a][3] : w[a][7];
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(dst + (size_t)a * 16384), "r"(x0), "r"(x1), "r"(x2), "r"(x3),
+                     "r"(x4), "r"(x5), "r"(x6), "r"(x7) : "memory");
+      }
     }
     mu_part[((size_t)split * p + j) * mc + m] = acc;
     return;

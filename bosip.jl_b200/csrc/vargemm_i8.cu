@@ -93,7 +93,7 @@ struct I8Args {
   double* q_part;         // [nsub][p][mc]
   long long mc;
   size_t b_per_out;       // bytes of B per output
-  int KB, T64, mtA, m_tiles, p, nsub, n_items;
+  int KB, T64, mtA, m_tiles, p, nsub, n_items, N;
 };
 
 template <int S>
@@ -174,10 +174,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           const int nkb = (t >> 1) + 1;
           mbar_wait_b(t_empty, (tile_cnt & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          // k < min(N, 64 (t + 1)) are the only non-zero columns of this n-tile: the last k-block may need fewer than 4 k-steps
+          const int k_end = min(g.N, I8_BN * (t + 1));
           for (int kb = 0; kb < nkb; ++kb) {
             const uint32_t bs = b_cnt & 1;
             mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1);
             const uint32_t b_addr = sB_u + bs * (uint32_t)Cfg::B_SET;
+            const int nks = min(4, (k_end - kb * I8_BK + 31) >> 5);
 #pragma unroll
             for (int a = 0; a < S; ++a) {
               const uint32_t as = a_cnt % Cfg::A_SLOTS;
@@ -186,12 +189,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
               const uint32_t a_addr = sA_u + as * (uint32_t)I8_A_TILE;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t da = umma_desc_sw128(a_addr + ks * 32);
+                if (ks < nks) {
+                  const uint64_t da = umma_desc_sw128(a_addr + ks * 32);
 #pragma unroll
-                for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> groups' columns 64 (c0 - a) ..
-                  const int nb = (S - c0) < 4 ? (S - c0) : 4;
-                  const uint64_t db = umma_desc_sw128(b_addr + (uint32_t)c0 * I8_B_TILE + ks * 32);
-                  umma_i8(tmem + (uint32_t)(64 * (c0 - a)), da, db, umma_idesc_u8s8(I8_BM, 64 * nb), (kb | ks | a) ? 1u : 0u);
+                  for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> group columns 64 (c0 - a) ..
+                    const int nb = (S - c0) < 4 ? (S - c0) : 4;
+                    umma_i8(tmem + (uint32_t)(64 * (c0 - a)), da, umma_desc_sw128(b_addr + (uint32_t)c0 * I8_B_TILE + ks * 32),
+                            umma_idesc_u8s8(I8_BM, 64 * nb), (kb | ks | a) ? 1u : 0u);
+                  }
                 }
               }
               umma_commit(&a_empty[as]);
@@ -380,7 +385,7 @@ int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int64_t mc, in
   I8Args a;
   a.A = Ks8; a.B = gp->LinvI8; a.cs = gp->cscale; a.q_part = q_part; a.mc = mc; a.b_per_out = gp->i8_b_per_out;
   a.KB = (gp->N + I8_BK - 1) / I8_BK; a.T64 = gp->i8_T64; a.mtA = (int)(mc / I8_BM); a.m_tiles = (int)m_tiles; a.p = gp->p;
-  a.nsub = i8_nsub(gp); a.n_items = (int)(m_tiles * gp->p * a.nsub);
+  a.N = gp->N; a.nsub = i8_nsub(gp); a.n_items = (int)(m_tiles * gp->p * a.nsub);
   switch (gp->i8_S) {
     case 6: BOSIP_TRY(launch_i8<6>(ctx, a, st)); break;
     case 7: BOSIP_TRY(launch_i8<7>(ctx, a, st)); break;

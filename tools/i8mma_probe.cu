@@ -186,6 +186,68 @@ static void run_peak(int blocks, int iters, int nacc) {
          2.0 * macs / (best * 1e-3) / 1e12, macs / blocks / (best * 1e-3) / 1.965e9);
 }
 
+
+// ---------------------------------------------------------------- pattern kernel: the per-k-step MMA sequence of the S-slice engine
+// mode 0: chunks of <= 4 slices from the top (4+3, 4+2, 4+1, 4, 3, 2, 1); mode 1: balanced halves (4+3, 3+3, 3+2, 4, 3, 2, 1)
+__global__ void __launch_bounds__(128) pattern_kernel(int iters, int S, int mode, int nmax) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  unsigned char* sA = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = sA + 4 * 16384;
+  for (int i = tid; i < (4 * 16384 + 8 * 8192) / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (tid == 0) { mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    for (int it = 0; it < iters; ++it) {
+      const int ks = it & 3;
+      for (int a = 0; a < S; ++a) {
+        const uint64_t da = make_desc(smem_u32(sA + (a & 3) * 16384) + ks * 32);
+        const int cnt = S - a;
+        if (mode == 2) {  // single-N sweep: one MMA of N = nmax per "row"
+          mma_i8(tb, da, make_desc(smem_u32(sB) + ks * 32), make_idesc(128, nmax), 1u);
+          continue;
+        }
+        int n0 = cnt <= 4 ? cnt : (mode == 0 ? 4 : (cnt + 1) / 2), n1 = cnt - n0;
+        mma_i8(tb, da, make_desc(smem_u32(sB + a * 8192) + ks * 32), make_idesc(128, 64 * n0), 1u);
+        if (n1 > 0) mma_i8(tb + 64 * n0, da, make_desc(smem_u32(sB + (a + n0) * 8192) + ks * 32), make_idesc(128, 64 * n1), 1u);
+      }
+    }
+    mma_commit(&done);
+    mbar_wait(&done, 0, 4);
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
+}
+
+static void run_pattern(int blocks, int iters, int S, int mode, int nmax) {
+  const size_t smem = 4 * 16384 + 8 * 8192 + 1024;
+  CK(cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  pattern_kernel<<<blocks, 128, smem>>>(50, S, mode, nmax);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(a));
+    pattern_kernel<<<blocks, 128, smem>>>(iters, S, mode, nmax);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+  }
+  const double clk = best * 1e-3 * 1.965e9 / iters;
+  if (mode == 2) printf("single N=%d: %.1f clk per MMA (M=128,K=32)\n", nmax, clk / S);
+  else printf("pattern S=%d mode=%d: %.1f clk per k-step (%d pairs; ideal %.0f)\n", S, mode, clk, S * (S + 1) / 2, S * (S + 1) / 2 * 32.0);
+}
+
 int main(int argc, char** argv) {
   int rc = 0;
   rc |= run_check<128>(1);
@@ -200,5 +262,7 @@ int main(int argc, char** argv) {
   run_peak<128>(sms, 20000, 4);
   run_peak<256>(sms, 10000, 2);
   run_peak<64>(sms, 20000, 4);
+  for (int n = 32; n <= 256; n += 32) run_pattern(sms, 4000, 4, 2, n);
+  for (int S = 6; S <= 8; ++S) for (int mode = 0; mode < 2; ++mode) run_pattern(sms, 2000, S, mode, 0);
   return 0;
 }

@@ -8,6 +8,8 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 128 * 4
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 ctx = bb.Context(0)
+if os.environ.get("BOSIP_ENGINE", "fp64") == "int8":
+    ctx.set_variance_engine("int8", int(os.environ.get("BOSIP_SLICES", "0")))
 pr = bb.synth.make_problem(name)
 model = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma)
 like = bb.NormalLikelihood(pr.z_obs, pr.std_obs); prior = bb.ProductPrior(pr.prior_kind, pr.prior_params)
