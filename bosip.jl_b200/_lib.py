@@ -16,7 +16,7 @@ WANT_APPROX, WANT_MEAN, WANT_VAR = 1, 2, 4
 ACQ_MAXVAR, ACQ_LOGMAXVAR = 0, 1
 PRIOR_UNIFORM, PRIOR_NORMAL, PRIOR_TRUNCNORMAL = 0, 1, 2
 CAND_POINTS, CAND_PHILOX, CAND_GRID = 0, 1, 2
-VAR_FP64, VAR_INT8 = 0, 1
+VAR_FP64, VAR_INT8, VAR_AUTO = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -128,9 +128,9 @@ class Context:
     def set_chunk(self, max_points: int):
         self._check(self.lib.bosip_b200_set_chunk(self.h, int(max_points)))
 
-    def set_variance_engine(self, engine: str = "fp64", slices: int = 0):
-        """'fp64' (DMMA) or 'int8' (tcgen05 INT8 on error-free byte slices; `slices` in 6..8, 0 = 7)."""
-        code = {"fp64": L.VAR_FP64, "int8": L.VAR_INT8}[engine]
+    def set_variance_engine(self, engine: str = "auto", slices: int = 0):
+        """'fp64' (DMMA), 'int8' (tcgen05 INT8 on error-free byte slices; `slices` in 6..8, 0 = 7) or 'auto' (int8 for N >= 128)."""
+        code = {"fp64": L.VAR_FP64, "int8": L.VAR_INT8, "auto": L.VAR_AUTO}[engine]
         self._check(self.lib.bosip_b200_set_variance_engine(self.h, code, int(slices)))
 
     def int8_peak(self) -> float:

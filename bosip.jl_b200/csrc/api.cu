@@ -191,7 +191,9 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   const bool gen = (sw.xq == nullptr);
 
   // ---- variance engine (FP64 DMMA or INT8 tcgen05 with error-free slicing)
-  const bool i8 = sw.need_var && ctx->var_engine == BOSIP_B200_VAR_INT8;
+  // AUTO: the INT8 engine pays off once the contraction is more than a tile deep; below that the FP64 kernel is as fast
+  bool i8 = sw.need_var && (ctx->var_engine == BOSIP_B200_VAR_INT8 || (ctx->var_engine == BOSIP_B200_VAR_AUTO && gp->N >= 128));
+  if (i8 && ctx->var_engine == BOSIP_B200_VAR_AUTO && (double)gp->N * ctx->var_slices * 255.0 * 128.0 >= 2147483647.0) i8 = false;
   const int S8 = ctx->var_slices, KB8 = (gp->N + 127) / 128;
   int nsub8 = 1;
   if (i8) {
@@ -200,9 +202,9 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   }
 
   // ---- n-split of the cross-kernel so that its shared-memory footprint allows >= 4 CTAs per SM
-  // (the INT8 slice writer walks 32 training points per iteration: spans are multiples of 32 there)
+  // (the INT8 slice writer walks 32 training points per iteration: spans are multiples of 32)
   static const int kstar_smem_kb = getenv("BOSIP_KSTAR_SMEM_KB") ? atoi(getenv("BOSIP_KSTAR_SMEM_KB")) : 56;  // dev A/B switch
-  const int span_q = i8 ? 32 : 16;
+  const int span_q = 32;  // same partition for every engine and for the mean-only path: the mean stays bit-identical across them
   int nspan = (int)((kstar_smem_kb * 1024) / (8 * (gp->dp + 1))) & ~(span_q - 1);
   nspan = std::max(span_q, std::min(nspan, (int)round_up(Ns, span_q)));
   int nsplit = (Ns + nspan - 1) / nspan;
@@ -405,6 +407,11 @@ int bosip_b200_init(int device, bosip_b200_ctx** out) {
   bosip_b200_ctx* h = new bosip_b200_ctx();
   Ctx* ctx = &h->c;
   ctx->device = device; ctx->sms = prop.multiProcessorCount;
+  ctx->var_engine = BOSIP_B200_VAR_AUTO;
+  if (const char* e = getenv("BOSIP_B200_VAR_ENGINE")) {  // process-wide default, e.g. to run a whole test suite on one engine
+    if (!strcmp(e, "fp64")) ctx->var_engine = BOSIP_B200_VAR_FP64;
+    else if (!strcmp(e, "int8")) ctx->var_engine = BOSIP_B200_VAR_INT8;
+  }
   bool ok = cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -449,7 +456,8 @@ int bosip_b200_launch_count(bosip_b200_ctx* h, int64_t* out) {
 
 int bosip_b200_set_variance_engine(bosip_b200_ctx* h, int engine, int slices) {
   API_LOCK(h);
-  if (engine != BOSIP_B200_VAR_FP64 && engine != BOSIP_B200_VAR_INT8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown variance engine");
+  if (engine != BOSIP_B200_VAR_FP64 && engine != BOSIP_B200_VAR_INT8 && engine != BOSIP_B200_VAR_AUTO)
+    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown variance engine");
   if (slices == 0) slices = 7;
   if (slices < 6 || slices > 8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "slices must be 6, 7 or 8 (0 = default)");
   ctx->var_engine = engine; ctx->var_slices = slices;

@@ -81,6 +81,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
 __device__ __forceinline__ double i32_to_f64(uint32_t v) {  // exact: 2^52 + 2^31 + v as a bit pattern, minus the offset
   return __hiloint2double(0x43300000, (int)(v ^ 0x80000000u)) - 4503601774854144.0;
 }
@@ -226,17 +234,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         if (i8_subset(t, g.T64, g.nsub) != sub) continue;
         mbar_wait_b(t_full, tile_cnt & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        double w[32];
-        uint32_t v[32];
-        // Horner from the least significant group: group gi lives at columns 64 (S-1-gi)
-        tmem_ld32(taddr, v);  // gi = S-1
+        // Horner from the least significant group (group gi lives at columns 64 (S-1-gi)), 16 columns at a time
+        double w[2][16];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) w[c] = i32_to_f64(v[c]);
+        for (int cq = 0; cq < 2; ++cq) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)(16 * cq), v);  // gi = S-1
 #pragma unroll
-        for (int gi = S - 2; gi >= 0; --gi) {
-          tmem_ld32(taddr + (uint32_t)(64 * (S - 1 - gi)), v);
+          for (int c = 0; c < 16; ++c) w[cq][c] = i32_to_f64(v[c]);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) w[c] = fma(w[c], 0.00390625, i32_to_f64(v[c]));
+          for (int gi = S - 2; gi >= 0; --gi) {
+            tmem_ld16(taddr + (uint32_t)(64 * (S - 1 - gi) + 16 * cq), v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) w[cq][c] = fma(w[cq][c], 0.00390625, i32_to_f64(v[c]));
+          }
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncwarp();
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         const double* cst = csj + (size_t)t * I8_BN + 32 * half;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const double x = w[c] * __ldg(cst + c);
+          const double x = w[c >> 4][c & 15] * __ldg(cst + c);
           rs = fma(x, x, rs);
         }
       }

@@ -141,6 +141,7 @@ int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
  * Both satisfy the 1e-10 parity bound; results differ in the last bits. */
 #define BOSIP_B200_VAR_FP64 0
 #define BOSIP_B200_VAR_INT8 1
+#define BOSIP_B200_VAR_AUTO 2 /* default: INT8 for N >= 128 training points, FP64 below */
 int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
 /* Measured issue-rate ceiling of tcgen05.mma kind::i8 (M=128, N=256, operands resident in shared memory) on all SMs,
  * in TOPS counting 2 ops per multiply-accumulate: the roofline denominator of the INT8 engine. */

@@ -1,0 +1,139 @@
+"""GPU: the INT8 (tcgen05, error-free byte slicing) variance engine through the C ABI vs the oracle and vs the FP64 (DMMA)
+engine: same parity gates as tests/test_gpu_parity.py, ragged shapes around the 64/128 tile edges, chunk invariance,
+queries on top of training points (worst cancellation), BI ensembles, option errors."""
+import numpy as np
+import pytest
+
+from oracle import bosip_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture()
+def engine(ctx):
+    """Yields a setter; always restores the default (auto) engine."""
+    yield ctx.set_variance_engine
+    ctx.set_variance_engine("auto")
+
+
+def _var_err(var, ovar, kxx):
+    return float(np.max(np.abs(var - ovar) / (np.abs(ovar) + 1e-3 * kxx[:, None])))
+
+
+def _problem(bb, name, M, seed=5):
+    pr = bb.synth.make_problem(name)
+    rng = np.random.default_rng(seed)
+    Xq = rng.uniform(pr.lb[:, None], pr.ub[:, None], size=(pr.d, M))
+    n = min(48, pr.N)
+    Xq[:, :n] = pr.X[:, :n]                 # exactly on training points: sigma^2 = alpha^2 - q cancels almost completely
+    Xq[:, n:2 * n] = pr.X[:, :n] + 1e-7
+    model = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma)
+    ofit = orc.gp_fit(pr.kernel_id, pr.X, pr.Y, pr.lam, pr.alpha, pr.sigma)
+    return pr, model, ofit, Xq
+
+
+@pytest.mark.parametrize("name,M", [("C2", 20000), ("C3", 20000)])
+@pytest.mark.parametrize("slices", [7, 8])
+def test_int8_engine_vs_oracle_and_fp64(bb, ctx, engine, name, M, slices):
+    pr, model, ofit, Xq = _problem(bb, name, M)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    engine("fp64")
+    mu0, var0 = post.mean_and_var(Xq)
+    engine("int8", slices)
+    mu1, var1 = post.mean_and_var(Xq)
+    kxx = pr.alpha ** 2
+    assert np.array_equal(mu0, mu1)                       # the mean path does not depend on the engine
+    assert _var_err(var1, ovar, kxx) < TOL
+    assert _var_err(var1, var0, kxx) < TOL
+    assert _var_err(var1, ovar, kxx) < 4 * _var_err(var0, ovar, kxx) + 1e-12   # as accurate as plain Float64
+    # fused closures on the INT8 engine
+    like = bb.NormalLikelihood(pr.z_obs, pr.std_obs); prior = bb.ProductPrior(pr.prior_kind, pr.prior_params)
+    res = bb.posterior_eval(post, like, prior, Xq, 7)
+    ores = orc.posterior_eval(ofit, orc.NormalLikelihood(pr.z_obs, pr.std_obs),
+                              orc.ProductPrior(list(pr.prior_kind), [list(q) for q in pr.prior_params]), Xq)
+    fin = np.isfinite(ores["log_post_var"]) & np.isfinite(res["log_post_var"])
+    assert np.sum(np.isfinite(ores["log_post_var"]) != np.isfinite(res["log_post_var"])) <= 1e-3 * M + 1
+    assert np.all(np.abs(res["log_post_var"][fin] - ores["log_post_var"][fin]) <= TOL * np.abs(ores["log_post_var"][fin]) + 1e-7)
+    np.testing.assert_allclose(res["log_post_mean"][np.isfinite(ores["log_post_mean"])],
+                               ores["log_post_mean"][np.isfinite(ores["log_post_mean"])], rtol=TOL)
+
+
+@pytest.mark.parametrize("kernel_id", [0, 1, 2])
+@pytest.mark.parametrize("d,p,N,M", [(1, 1, 1, 1), (3, 2, 63, 127), (3, 2, 64, 128), (4, 3, 65, 129), (2, 1, 127, 300), (2, 2, 128, 256),
+                                       (6, 1, 129, 1000), (5, 2, 257, 500), (10, 1, 400, 777)])
+def test_int8_ragged_shapes(bb, ctx, engine, kernel_id, d, p, N, M):
+    rng = np.random.default_rng(100 * kernel_id + N)
+    X = rng.uniform(-5, 5, (d, N)); Y = rng.standard_normal((p, N))
+    lam = rng.uniform(1, 4, (d, p)); alpha = rng.uniform(0.5, 2, p); sigma = 0.05 * alpha
+    Xq = rng.uniform(-5, 5, (d, M))
+    model = bb.GaussianProcess(kernel_id, lam, alpha, sigma)
+    post = bb.model_posterior(model, X, Y, ctx=ctx)
+    ofit = orc.gp_fit(kernel_id, X, Y, lam, alpha, sigma)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    engine("int8", 7)
+    mu, var = post.mean_and_var(Xq)
+    assert var.shape == (p, M)
+    assert _var_err(var, ovar, alpha ** 2) < TOL
+    scale = np.max(np.abs(omu))
+    assert np.max(np.abs(mu - omu) / (np.abs(omu) + 1e-3 * scale)) < 1e-9
+
+
+def test_int8_chunking_is_invisible(bb, ctx, engine):
+    pr, model, ofit, Xq = _problem(bb, "C2", 3001)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    engine("int8", 7)
+    mu0, var0 = post.mean_and_var(Xq)
+    try:
+        for chunk in (128, 640, 1000):
+            ctx.set_chunk(chunk)
+            mu, var = post.mean_and_var(Xq)
+            assert np.array_equal(mu, mu0) and np.array_equal(var, var0)
+    finally:
+        ctx.set_chunk(0)
+    import torch
+    Xd = torch.from_numpy(np.ascontiguousarray(Xq.T)).cuda().t()
+    mu_d, var_d = post.mean_and_var(Xd)
+    assert np.array_equal(mu_d.cpu().numpy(), mu0) and np.array_equal(var_d.cpu().numpy(), var0)
+
+
+def test_auto_engine_and_option_errors(bb, ctx, engine):
+    pr, model, ofit, Xq = _problem(bb, "C2", 2000)      # N = 200 >= 128: auto picks the INT8 engine
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    engine("auto")
+    _, va = post.mean_and_var(Xq)
+    engine("int8", 0)
+    _, vi = post.mean_and_var(Xq)
+    assert np.array_equal(va, vi)
+    pr1, model1, ofit1, Xq1 = _problem(bb, "C1", 500)   # N = 20 < 128: auto stays on the FP64 engine
+    post1 = bb.model_posterior(model1, pr1.X, pr1.Y, ctx=ctx)
+    engine("auto")
+    _, va = post1.mean_and_var(Xq1)
+    engine("fp64")
+    _, vf = post1.mean_and_var(Xq1)
+    assert np.array_equal(va, vf)
+    with pytest.raises(bb.BosipB200Error):
+        ctx.set_variance_engine("int8", 5)
+    with pytest.raises(bb.BosipB200Error):
+        ctx.set_variance_engine("int8", 9)
+    assert ctx.int8_peak() > 1000.0                      # TOPS; the tcgen05 path is alive
+
+
+def test_int8_bi_ensemble_matches_fp64(bb, ctx, engine):
+    pr = bb.synth.make_problem("C2")
+    rng = np.random.default_rng(3)
+    models = [bb.GaussianProcess(pr.kernel_id, pr.lam * f, pr.alpha, pr.sigma) for f in (0.8, 1.0, 1.3)]
+    posts = [bb.model_posterior(m, pr.X, pr.Y, ctx=ctx) for m in models]
+    like = bb.NormalLikelihood(pr.z_obs, pr.std_obs); prior = bb.ProductPrior(pr.prior_kind, pr.prior_params)
+    Xq = rng.uniform(pr.lb[:, None], pr.ub[:, None], size=(pr.d, 4000))
+    engine("fp64")
+    r0 = bb.posterior_eval(posts, like, prior, Xq, 7)
+    engine("int8", 7)
+    r1 = bb.posterior_eval(posts, like, prior, Xq, 7)
+    np.testing.assert_array_equal(r0["log_approx_post"], r1["log_approx_post"])   # plug-in closure: no variance involved
+    np.testing.assert_allclose(r0["log_post_mean"], r1["log_post_mean"], rtol=TOL)
+    a, b = r0["log_post_var"], r1["log_post_var"]
+    fin = np.isfinite(a) & np.isfinite(b)
+    assert np.sum(np.isfinite(a) != np.isfinite(b)) <= 4
+    assert np.all(np.abs(a[fin] - b[fin]) <= TOL * np.abs(a[fin]) + 1e-7)

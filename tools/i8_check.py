@@ -69,8 +69,9 @@ def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     ctx = bb.Context(0)
     if len(sys.argv) > 1 and sys.argv[1] == "time":
-        for cfg in sys.argv[2:] or ["C3"]:
-            timing(cfg, {"C3": 148 * 128 * 8, "C2": 10 ** 6, "C5": 148 * 128 * 2}[cfg], ctx, slices_list=(7,))
+        for spec in sys.argv[2:] or ["C3"]:
+            cfg, _, m = spec.partition(":")
+            timing(cfg, int(m) if m else {"C3": 148 * 128 * 8, "C2": 10 ** 6, "C5": 148 * 128 * 2}[cfg], ctx, slices_list=(7,))
         return
     print(json.dumps({"int8_peak_tops": ctx.int8_peak(), **ctx.fp64_peak()}), flush=True)
     compare("C1", 1000, ctx)
