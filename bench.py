@@ -12,9 +12,14 @@ scaling: the full 1e8 set at 8 GPUs).  A step = ONE pass of the hot path over th
           written to HBM, argmax of the acquisition taken in the same sweep, per-rank winners all-gathered.
   e2e   : the same call through the public API with HOST buffers: pinned-host candidates in, three pinned-host output
           vectors back, H2D/D2H inside the timed region.
-One JSON line on stdout (rank 0).  `roofline` is for the dominant kernel (the FP64 DMMA variance GEMM); its peak is the
-DMMA microbenchmark measured in this run because MEASURED_PEAKS.json holds no FP64 figure.  `cpu_baseline` is the oracle's
-restatement of the reference CPU path (NumPy/OpenBLAS, all host cores) on a bounded sample of the same workload.
+One JSON line on stdout (rank 0).  `roofline` is for the dominant kernel, the variance contraction K* . L^-T + row sums:
+  --engine auto|int8 (default): `vargemm_i8_kernel` -- tcgen05 INT8 tensor cores on error-free byte slices of both operands;
+          achieved = the INT8 operations the slicing scheme needs (S(S+1)/2 slice GEMMs over the triangular N(N+1)/2 MACs) per
+          second, peak = the tcgen05 kind::i8 issue-rate ceiling measured in this run (bosip_b200_int8_peak);
+  --engine fp64: `vargemm_kernel` (mma.sync FP64 DMMA); peak = the DMMA microbenchmark measured in this run.
+MEASURED_PEAKS.json holds neither an INT8 nor an FP64 figure.  `roofline.fp64_equivalent_tflops` is SURVEY 8(d)'s F_var per
+second for either engine.  `cpu_baseline` is the oracle's restatement of the reference CPU path (NumPy/OpenBLAS, all host
+cores) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -103,7 +108,7 @@ def config_dict(n_gpus):
                         "per GPU per step (1e8 at 8 GPUs), outputs log_approx_post/log_post_mean/log_post_var + MaxVar argmax",
             "points_per_gpu_per_step": PER_GPU, "global_points_per_step": PER_GPU * n_gpus, "d": 5, "p": 4, "N": 1000,
             "kernel": "Matern52", "parallelism": f"candidate-range shard x{n_gpus}, argmax all-gather",
-            "l2": "inputs (500 MB candidates + 2.4 GB K* workspace per chunk sweep) exceed the 126 MB L2; no explicit flush needed"}
+            "l2": "inputs (500 MB candidates + 2.1-2.4 GB K* workspace per chunk sweep) exceed the 126 MB L2; no explicit flush needed"}
 
 
 def run_reference(args, rank):
@@ -138,6 +143,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="auto", choices=["auto", "int8", "fp64"], help="variance engine (auto = int8 at N=1000)")
+    ap.add_argument("--slices", type=int, default=0, help="byte slices of the INT8 engine (0 = default 7)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -162,7 +169,11 @@ def main():
     ctx = bb.Context(local)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_variance_engine(args.engine, args.slices)
+    use_i8 = args.engine != "fp64"
+    S = args.slices or 7
     peak = ctx.fp64_peak()
+    peak["int8_tops_burst"], peak["int8_tops_sustained"] = ctx.int8_peak(sustained=True)
     post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)           # every rank conditions the same seeded inputs
     start, count = bb.parallel.shard_range(PER_GPU * world, rank, world)
     src = bb.CandidateSource.philox(SEED, pr.lb, pr.ub, PER_GPU * world)
@@ -235,26 +246,42 @@ def main():
         vg = tm["var_gemm"]
         pts_per_launch = args.steps * count / max(1, vg["launches"])
         vg_ms = vg["ms"] / max(1, vg["launches"])
-        achieved = fl["var"] * pts_per_launch / (vg_ms * 1e-3) * 1e-12
+        fp64_equiv = fl["var"] * pts_per_launch / (vg_ms * 1e-3) * 1e-12
+        tname = "vargemm_i8_traffic.json" if use_i8 else "vargemm_traffic.json"
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "vargemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", tname)
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        if use_i8:
+            int8_ops_per_point = S * (S + 1) // 2 * fl["var"]        # every kept slice pair repeats the triangular contraction
+            achieved = int8_ops_per_point * pts_per_launch / (vg_ms * 1e-3) * 1e-12
+            roof = {"kernel": f"vargemm_i8_kernel<{S}> (tcgen05 INT8 K* . L^-T on {S} byte slices per operand, TMEM accumulators, FP64 Horner "
+                              "epilogue + row sum of squares)", "bound": "tensor", "achieved": achieved, "peak": peak["int8_tops_sustained"],
+                    "unit": "TOP/s", "frac": achieved / peak["int8_tops_sustained"], "frac_of_burst_peak": achieved / peak["int8_tops_burst"],
+                    "traffic": traffic,
+                    "peak_source": "tcgen05.mma kind::i8 M=128 N=256 issue-rate microbenchmark measured in this run (bosip_b200_int8_peak): the "
+                                   "sustained figure (2 s back to back under the 1 kW cap) because the kernel is timed inside a long step; "
+                                   "MEASURED_PEAKS.json has no INT8 figure (2 x its bf16 sustained/burst would be 2807/3335); nominal dense INT8 4500",
+                    "algorithmic_int8_ops_per_point": int8_ops_per_point, "slice_pairs": S * (S + 1) // 2}
+        else:
+            achieved = fp64_equiv
+            roof = {"kernel": "vargemm_kernel (FP64 DMMA K* . L^-T + row sum of squares)", "bound": "tensor", "achieved": achieved,
+                    "peak": peak["dmma_tflops"], "unit": "TFLOP/s", "frac": achieved / peak["dmma_tflops"], "traffic": traffic,
+                    "peak_source": "DMMA m8n8k4 microbenchmark measured in this run (bosip_b200_fp64_peak); MEASURED_PEAKS.json has no FP64 figure; datasheet 37 TFLOP/s"}
+        roof.update({"algorithmic_flops_per_point": fl["var"], "fp64_equivalent_tflops": fp64_equiv,
+                     "fp64_equivalent_vs_dmma_peak": fp64_equiv / peak["dmma_tflops"], "points_per_launch": pts_per_launch,
+                     "ms_per_launch": vg_ms, "launches": vg["launches"], "share_of_step": vg["ms"] / ms_total})
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_dict(world),
+            "data": "synthetic", "config": dict(config_dict(world), variance_engine=("int8x%d" % S) if use_i8 else "fp64"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(count * pr.d * 8), "d2h_bytes_per_step": int(count * 3 * 8),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "vargemm_kernel (FP64 DMMA K* . L^-T + row sum of squares)", "bound": "tensor", "achieved": achieved,
-                         "peak": peak["dmma_tflops"], "unit": "TFLOP/s", "frac": achieved / peak["dmma_tflops"], "traffic": traffic,
-                         "peak_source": "DMMA m8n8k4 microbenchmark measured in this run (bosip_b200_fp64_peak); MEASURED_PEAKS.json has no FP64 figure; datasheet 37 TFLOP/s",
-                         "algorithmic_flops_per_point": fl["var"], "points_per_launch": pts_per_launch, "ms_per_launch": vg_ms,
-                         "launches": vg["launches"], "share_of_step": vg["ms"] / ms_total},
+            "roofline": roof,
             "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in tm.items()},
-            "fp64_peaks": peak,
+            "measured_peaks": peak,
             "whole_path_tflops_as_written": sum(fl.values()) * value / world * 1e-12,
             "argmax": {"global_index": int(winner[0]), "value": float(winner[1])},
         }

@@ -133,11 +133,12 @@ class Context:
         code = {"fp64": L.VAR_FP64, "int8": L.VAR_INT8, "auto": L.VAR_AUTO}[engine]
         self._check(self.lib.bosip_b200_set_variance_engine(self.h, code, int(slices)))
 
-    def int8_peak(self) -> float:
-        """Measured tcgen05 INT8 issue-rate ceiling (TOPS, 2 ops per MAC) of this GPU: the INT8 engine's roofline denominator."""
-        a = C.c_double()
-        self._check(self.lib.bosip_b200_int8_peak(self.h, C.byref(a)))
-        return a.value
+    def int8_peak(self, sustained: bool = False):
+        """Measured tcgen05 INT8 issue-rate ceiling (TOPS, 2 ops per MAC) of this GPU: the INT8 engine's roofline denominator.
+        Returns the burst figure, or (burst, sustained-under-power-cap) when `sustained` (takes ~2 s)."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.bosip_b200_int8_peak(self.h, C.byref(a), C.byref(b) if sustained else None))
+        return (a.value, b.value) if sustained else a.value
 
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()

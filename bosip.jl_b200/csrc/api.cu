@@ -822,10 +822,10 @@ int bosip_b200_tv(bosip_b200_ctx* h, const double* lw, const double* a, const do
   return 0;
 }
 
-int bosip_b200_int8_peak(bosip_b200_ctx* h, double* tops) {
+int bosip_b200_int8_peak(bosip_b200_ctx* h, double* burst_tops, double* sustained_tops) {
   API_LOCK(h);
-  if (!tops) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "tops must not be NULL");
-  return i8_peak(ctx, tops);
+  if (!burst_tops) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "burst_tops must not be NULL");
+  return i8_peak(ctx, burst_tops, sustained_tops);
 }
 
 int bosip_b200_fp64_peak(bosip_b200_ctx* h, double* dmma, double* dfma) {

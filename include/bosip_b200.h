@@ -144,8 +144,9 @@ int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
 #define BOSIP_B200_VAR_AUTO 2 /* default: INT8 for N >= 128 training points, FP64 below */
 int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
 /* Measured issue-rate ceiling of tcgen05.mma kind::i8 (M=128, N=256, operands resident in shared memory) on all SMs,
- * in TOPS counting 2 ops per multiply-accumulate: the roofline denominator of the INT8 engine. */
-int bosip_b200_int8_peak(bosip_b200_ctx* ctx, double* tops);
+ * in TOPS counting 2 ops per multiply-accumulate: the roofline denominator of the INT8 engine.  burst = best of five 2.7 ms
+ * launches; sustained (optional, may be NULL; takes ~2 s) = the rate the part holds under its power cap. */
+int bosip_b200_int8_peak(bosip_b200_ctx* ctx, double* burst_tops, double* sustained_tops);
 
 /* ---- GP conditioning: replaces BOSS.model_posterior(bosip.problem)
  *      (src/posterior/log_posterior.jl:81,115,148,182,214) --------------------------------------------- */

@@ -68,6 +68,9 @@ def timing(name, M, ctx, slices_list=(7, 8)):
 def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     ctx = bb.Context(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "one":   # one comparison: one <cfg> <M> <slices>
+        compare(sys.argv[2], int(sys.argv[3]), ctx, slices_list=(int(sys.argv[4]),))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "time":
         for spec in sys.argv[2:] or ["C3"]:
             cfg, _, m = spec.partition(":")

@@ -248,6 +248,82 @@ static void run_pattern(int blocks, int iters, int S, int mode, int nmax) {
   else printf("pattern S=%d mode=%d: %.1f clk per k-step (%d pairs; ideal %.0f)\n", S, mode, clk, S * (S + 1) / 2, S * (S + 1) / 2 * 32.0);
 }
 
+// ---------------------------------------------------------------- compile-time MMA sequences (tight issue loop): cost model of tcgen05.mma kind::i8
+// PAT 0: the engine's S=7 k-step (256+192, 256+128, 256+64, 256, 192, 128, 64); 1: 7 x N=256; 2: 14 x N=128; 3: 28 x N=64;
+// 4: 9 x N=192 + 1 x 64; 5: S=7 k-step with every MMA on its own accumulator columns (no shared D)
+template <int PAT>
+__global__ void __launch_bounds__(128) seq_kernel(int iters) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  unsigned char* sA = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = sA + 7 * 16384;
+  for (int i = tid; i < (7 * 16384 + 7 * 8192) / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (tid == 0) { mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t ko = (it & 3) * 32;
+      if (PAT == 0 || PAT == 5) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+          const uint64_t da = make_desc(a0 + a * 16384 + ko);
+#pragma unroll
+          for (int c0 = a; c0 < 7; c0 += 4) {
+            const int nb = (7 - c0) < 4 ? (7 - c0) : 4;
+            mma_i8(tb + (PAT == 0 ? 64 * (c0 - a) : 0), da, make_desc(b0 + c0 * 8192 + ko), make_idesc(128, 64 * nb), 1u);
+          }
+        }
+      } else if (PAT == 1) {
+#pragma unroll
+        for (int a = 0; a < 7; ++a) mma_i8(tb + (a & 1) * 256, make_desc(a0 + a * 16384 + ko), make_desc(b0 + (a % 4) * 8192 + ko), make_idesc(128, 256), 1u);
+      } else if (PAT == 2) {
+#pragma unroll
+        for (int a = 0; a < 14; ++a) mma_i8(tb + (a & 3) * 128, make_desc(a0 + (a % 7) * 16384 + ko), make_desc(b0 + (a % 6) * 8192 + ko), make_idesc(128, 128), 1u);
+      } else if (PAT == 3) {
+#pragma unroll
+        for (int a = 0; a < 28; ++a) mma_i8(tb + (a & 7) * 64, make_desc(a0 + (a % 7) * 16384 + ko), make_desc(b0 + (a % 7) * 8192 + ko), make_idesc(128, 64), 1u);
+      } else if (PAT == 4) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) mma_i8(tb + (a & 1) * 192, make_desc(a0 + (a % 7) * 16384 + ko), make_desc(b0 + (a % 5) * 8192 + ko), make_idesc(128, 192), 1u);
+        mma_i8(tb + 448, make_desc(a0 + ko), make_desc(b0 + ko), make_idesc(128, 64), 1u);
+      }
+    }
+    mma_commit(&done);
+    mbar_wait(&done, 0, 5);
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
+}
+
+template <int PAT>
+static void run_seq(int blocks, int iters, const char* what) {
+  const size_t smem = 7 * 16384 + 7 * 8192 + 1024;
+  CK(cudaFuncSetAttribute(seq_kernel<PAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  seq_kernel<PAT><<<blocks, 128, smem>>>(50);
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(a));
+    seq_kernel<PAT><<<blocks, 128, smem>>>(iters);
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+  }
+  printf("seq %d (%s): %.1f clk per k-step (1792 output columns; math floor 896)\n", PAT, what, best * 1e-3 * 1.965e9 / iters);
+}
+
 int main(int argc, char** argv) {
   int rc = 0;
   rc |= run_check<128>(1);
@@ -262,6 +338,8 @@ int main(int argc, char** argv) {
   run_peak<128>(sms, 20000, 4);
   run_peak<256>(sms, 10000, 2);
   run_peak<64>(sms, 20000, 4);
+  run_seq<0>(sms, 3000, "S=7 engine pattern"); run_seq<5>(sms, 3000, "same, all on D column 0"); run_seq<1>(sms, 3000, "7 x N=256");
+  run_seq<2>(sms, 3000, "14 x N=128"); run_seq<3>(sms, 3000, "28 x N=64"); run_seq<4>(sms, 3000, "9 x N=192 + N=64");
   for (int n = 32; n <= 256; n += 32) run_pattern(sms, 4000, 4, 2, n);
   for (int S = 6; S <= 8; ++S) for (int mode = 0; mode < 2; ++mode) run_pattern(sms, 2000, S, mode, 0);
   return 0;
