@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", default="auto", choices=["auto", "int8", "fp64"], help="variance engine (auto = int8 at N=1000)")
     ap.add_argument("--slices", type=int, default=0, help="byte slices of the INT8 engine (0 = default 7)")
+    ap.add_argument("--quick-peaks", action="store_true", help="skip the 2 s sustained INT8 peak loop (ncu launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -173,7 +174,10 @@ def main():
     use_i8 = args.engine != "fp64"
     S = args.slices or 7
     peak = ctx.fp64_peak()
-    peak["int8_tops_burst"], peak["int8_tops_sustained"] = ctx.int8_peak(sustained=True)
+    if args.quick_peaks:
+        peak["int8_tops_burst"] = peak["int8_tops_sustained"] = ctx.int8_peak()
+    else:
+        peak["int8_tops_burst"], peak["int8_tops_sustained"] = ctx.int8_peak(sustained=True)
     post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)           # every rank conditions the same seeded inputs
     start, count = bb.parallel.shard_range(PER_GPU * world, rank, world)
     src = bb.CandidateSource.philox(SEED, pr.lb, pr.ub, PER_GPU * world)

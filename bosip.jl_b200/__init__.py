@@ -15,4 +15,8 @@ from .api import (B200CandidateAM, B200GPPosterior, BosipB200Error, BosipProblem
                   log_approx_marginal_likelihood, log_marginal_likelihood_mean, log_sq_likelihood_mean, compute_marginals_int,
                   generate_LHC, normalize_prob_vals, LogNormalLikelihood, NormalDiffLikelihood, NormalSumLikelihood, ExpLikelihood, bosip, DataLimit, IterLimit)
 
+from .sampling import (AEConfidence, AMIS, AMISSampler, AnalyticalFitter, NormalProposal, OptMMDMetric, amis_log_weights,  # noqa: F401,E402
+                       approx_cutoff_area, exp_weights, find_cutoff, mixture_pdf_sum, resample, sample_posterior,
+                       sample_posterior_pure, set_iou, weighted_moments, weighted_quantile)
+
 __version__ = "0.1.0"

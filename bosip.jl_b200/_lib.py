@@ -88,6 +88,14 @@ PROTOTYPES = {
     "bosip_b200_tv_stage2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double,
                                        C.c_double, c_double_p]),
     "bosip_b200_tv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "bosip_b200_mvnormal_sample": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    "bosip_b200_mixture_pdf_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_void_p, C.c_int64, C.c_int,
+                                             C.c_int, C.c_void_p]),
+    "bosip_b200_amis_log_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int, C.c_void_p]),
+    "bosip_b200_weighted_moments": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p, c_double_p,
+                                              c_double_p, C.c_void_p]),
+    "bosip_b200_resample": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
     "bosip_b200_fp64_peak": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "bosip_b200_math_selftest": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
     "bosip_b200_timing_reset": (C.c_int, [C.c_void_p, C.c_int]),

@@ -297,6 +297,24 @@ class ProductPrior:
     def _c(self, logprior_ptr=None):
         return L.Prior(self.d, self.kind.ctypes.data_as(L.c_int32_p), _dptr(self.params), logprior_ptr)
 
+    def logpdf(self, X) -> np.ndarray:
+        """logpdf(x_prior, x) per column of X (d x M), on the host: -Inf outside the support (Distributions semantics;
+        the device epilogue applies the same formulas inside the fused sweep, src/posterior/log_posterior.jl:228-229)."""
+        from scipy.special import erfc
+        X = np.asarray(X, dtype=np.float64).reshape(self.d, -1)
+        out = np.zeros(X.shape[1])
+        for k in range(self.d):
+            q, x = self.params[k], X[k]
+            if self.kind[k] == UNIFORM:
+                out += np.where((x >= q[0]) & (x <= q[1]), -math.log(q[1] - q[0]), -np.inf)
+            else:
+                lp = -0.5 * ((x - q[0]) / q[1]) ** 2 - 0.5 * math.log(2.0 * math.pi) - math.log(q[1])
+                if self.kind[k] == TRUNCNORMAL:
+                    tp = 0.5 * erfc(-(q[3] - q[0]) / q[1] / math.sqrt(2.0)) - 0.5 * erfc(-(q[2] - q[0]) / q[1] / math.sqrt(2.0))
+                    lp = np.where((x >= q[2]) & (x <= q[3]), lp - math.log(tp), -np.inf)
+                out += lp
+        return out
+
     def rand(self, n: int, rng: np.random.Generator) -> np.ndarray:
         """d x n samples (rand(x_prior, n), src/posterior/evidence.jl:21)."""
         from scipy.stats import truncnorm

@@ -822,6 +822,40 @@ int bosip_b200_tv(bosip_b200_ctx* h, const double* lw, const double* a, const do
   return 0;
 }
 
+int bosip_b200_mvnormal_sample(bosip_b200_ctx* h, int d, const double* mu, const double* L, uint64_t seed, int64_t offset, int64_t M,
+                               int mem, double* out) {
+  API_LOCK(h);
+  if (!mu || !L || !out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "mvnormal_sample: NULL argument");
+  return mvn_sample(ctx, d, mu, L, seed, offset, M, mem, out);
+}
+
+int bosip_b200_mixture_pdf_sum(bosip_b200_ctx* h, int d, int nq, const double* mus, const double* Linvs, const double* lognorm,
+                               const double* X, int64_t M, int mem, int accumulate, double* delta) {
+  API_LOCK(h);
+  if (!mus || !Linvs || !lognorm || !X || !delta) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "mixture_pdf_sum: NULL argument");
+  return mix_pdf_sum(ctx, d, nq, mus, Linvs, lognorm, X, M, mem, accumulate, delta);
+}
+
+int bosip_b200_amis_log_weights(bosip_b200_ctx* h, const double* log_p, const double* delta, double t, int64_t M, int mem, double* log_w) {
+  API_LOCK(h);
+  if (!log_p || !delta || !log_w) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "amis_log_weights: NULL argument");
+  return amis_log_weights(ctx, log_p, delta, t, M, mem, log_w);
+}
+
+int bosip_b200_weighted_moments(bosip_b200_ctx* h, int d, const double* X, const double* log_w, int64_t M, int mem, double* mean,
+                                double* cov, double* sums, double* ws) {
+  API_LOCK(h);
+  if (!X || !log_w || !mean || !cov) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "weighted_moments: NULL argument");
+  return weighted_moments(ctx, d, X, log_w, M, mem, mean, cov, sums, ws);
+}
+
+int bosip_b200_resample(bosip_b200_ctx* h, int d, const double* X, const double* ws, int64_t M, uint64_t seed, int64_t count, int mem,
+                        double* out, int64_t* idx) {
+  API_LOCK(h);
+  if (!X || !ws || !out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "resample: NULL argument");
+  return resample(ctx, d, X, ws, M, seed, count, mem, out, idx);
+}
+
 int bosip_b200_int8_peak(bosip_b200_ctx* h, double* burst_tops, double* sustained_tops) {
   API_LOCK(h);
   if (!burst_tops) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "burst_tops must not be NULL");

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <mutex>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "../../include/bosip_b200.h"
 
@@ -198,6 +200,14 @@ int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double*
 int tv_stage1(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* out4);
 int tv_stage2(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double eva,
               double evt, double* out2);
+// sampler.cu
+int mvn_sample(Ctx* ctx, int d, const double* mu, const double* L, uint64_t seed, int64_t offset, int64_t m, int mem, double* out);
+int mix_pdf_sum(Ctx* ctx, int d, int nq, const double* mus, const double* Linvs, const double* lognorm, const double* X, int64_t m, int mem,
+                int accumulate, double* delta);
+int amis_log_weights(Ctx* ctx, const double* logp, const double* delta, double t, int64_t m, int mem, double* logw);
+int weighted_moments(Ctx* ctx, int d, const double* X, const double* lw, int64_t m, int mem, double* mean, double* cov, double* sums,
+                     double* ws);
+int resample(Ctx* ctx, int d, const double* X, const double* ws, int64_t m, uint64_t seed, int64_t count, int mem, double* out, int64_t* idx);
 // peaks.cu
 int fp64_peak(Ctx* ctx, double* dmma, double* dfma);
 int math_selftest(Ctx* ctx, const double* x, int64_t n, double* e_fast, double* q_fast, double* e_ref, double* q_ref);

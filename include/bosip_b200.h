@@ -143,6 +143,32 @@ int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
 #define BOSIP_B200_VAR_INT8 1
 #define BOSIP_B200_VAR_AUTO 2 /* default: INT8 for N >= 128 training points, FP64 below */
 int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
+/* ---- AMIS importance sampler, inner loop (src/samplers/amis/amis_method.jl:26-83,126-134;
+ *      src/samplers/amis/proposal_distributions/normal.jl:75-100; src/sampling.jl:55-57).  The samples, log_P, Delta and
+ *      log_Omega can stay in HBM between iterations (mem = BOSIP_B200_DEVICE); log_pi(xs) is bosip_b200_posterior_eval. ---- */
+/* `rand(q, M)` for q = MvNormal(mu, L L'): x_i = mu + L z_i, z from Philox4x32-10 keyed by (seed, offset + i) + Box-Muller.
+ * mu (d) and L (d x d column-major, lower triangle read) are host pointers; out is d x M in `mem`. */
+int bosip_b200_mvnormal_sample(bosip_b200_ctx* ctx, int d, const double* mu, const double* L, uint64_t seed, int64_t offset,
+                               int64_t M, int mem, double* out);
+/* delta[m] (+)= sum_q pdf(MvNormal(mu_q, Sigma_q), x_m)  (amis_method.jl:52,66-68,74).  Host parameter arrays: mus d x nq,
+ * Linvs nq inverse Cholesky factors (d x d column-major, lower), lognorm[q] = -sum_i log L_q[i,i] - d/2 log(2 pi).
+ * accumulate = 0 overwrites delta. */
+int bosip_b200_mixture_pdf_sum(bosip_b200_ctx* ctx, int d, int nq, const double* mus, const double* Linvs, const double* lognorm,
+                               const double* X, int64_t M, int mem, int accumulate, double* delta);
+/* log_w[m] = log_p[m] - log(delta[m] / t)  (amis_method.jl:53,69,75) */
+int bosip_b200_amis_log_weights(bosip_b200_ctx* ctx, const double* log_p, const double* delta, double t, int64_t M, int mem,
+                                double* log_w);
+/* exp_weights (amis_method.jl:126-134) + AnalyticalFitter / estimate_parameters! (normal.jl:75-100): w = exp(log_w - max),
+ * mean = sum w x / V1, cov = sum w (x-mean)(x-mean)' / (V1 - V2/V1), V1 = sum w, V2 = sum w^2.  mean (d), cov (d x d) and
+ * sums (2: V1, V2; optional) are host outputs; ws (optional, M, in `mem`) receives the normalised weights w / V1.
+ * NaN or +Inf log-weights, or all weights zero, return BOSIP_B200_EDOMAIN ("AMIS: Numerical issues with sample weights."). */
+int bosip_b200_weighted_moments(bosip_b200_ctx* ctx, int d, const double* X, const double* log_w, int64_t M, int mem, double* mean,
+                                double* cov, double* sums, double* ws);
+/* resample(xs, ws, count) (src/sampling.jl:55-57): `count` draws with replacement, P(i) = ws[i] / sum ws; draw j uses the
+ * Philox uniform keyed by (seed, j).  out is d x count in `mem`; idx (optional, count, in `mem`) receives the chosen columns. */
+int bosip_b200_resample(bosip_b200_ctx* ctx, int d, const double* X, const double* ws, int64_t M, uint64_t seed, int64_t count, int mem,
+                        double* out, int64_t* idx);
+
 /* Measured issue-rate ceiling of tcgen05.mma kind::i8 (M=128, N=256, operands resident in shared memory) on all SMs,
  * in TOPS counting 2 ops per multiply-accumulate: the roofline denominator of the INT8 engine.  burst = best of five 2.7 ms
  * launches; sustained (optional, may be NULL; takes ~2 s) = the rate the part holds under its power cap. */

@@ -527,3 +527,115 @@ def cpu_baseline_posterior_maxvar(fit: GPFit, like, prior, Xq, chunk=65536, dedu
             out_v[c0:c0 + chunk] = 2.0 * lp + np.log(v)
         out_m[c0:c0 + chunk] = lp + log_L
     return out_a, out_m, out_v, int(np.argmax(out_v))
+
+
+# ------------------------------------------------------------------------------------------------ AMIS inner loop, confidence sets
+# (test infrastructure: restates /root/reference/src/samplers/amis/amis_method.jl:26-134, proposal_distributions/normal.jl:75-100,
+#  src/utils/confidence_set.jl:19-81, src/sampling.jl:55-57 and StatsBase's weighted quantile, which Distributions.weights feeds)
+def mvnormal_logpdf(mu, Sigma, X):
+    """logpdf(MvNormal(mu, Sigma), x) per column of X (d x M)."""
+    mu = np.asarray(mu, float); Sigma = np.asarray(Sigma, float); X = np.asarray(X, float).reshape(len(mu), -1)
+    Lc = np.linalg.cholesky(Sigma)
+    z = solve_triangular(Lc, X - mu[:, None], lower=True)
+    return -0.5 * np.sum(z * z, axis=0) - np.sum(np.log(np.diag(Lc))) - 0.5 * len(mu) * math.log(2.0 * math.pi)
+
+
+def exp_weights(log_ws):
+    """amis_method.jl:126-134"""
+    log_ws = np.asarray(log_ws, float)
+    M = np.max(log_ws)
+    if M == -np.inf:
+        raise RuntimeError("Sampling failed due to numerical issues with sample weights.")
+    ws = np.exp(log_ws - M)
+    return ws / np.sum(ws)
+
+
+def get_weights(log_ws):
+    """amis_method.jl:109-124"""
+    log_ws = np.asarray(log_ws, float)
+    if np.any(np.isnan(log_ws)) or np.any(log_ws == np.inf) or np.all(log_ws == -np.inf):
+        raise RuntimeError("AMIS: Numerical issues with sample weights.")
+    return exp_weights(log_ws)
+
+
+def estimate_parameters(xs, ws):
+    """estimate_parameters!(::NormalProposal, xs, ws) -- normal.jl:75-100; returns (mu, Sigma) or None when the estimate is unusable."""
+    xs = np.asarray(xs, float); ws = np.asarray(ws, float)
+    V1, V2 = np.sum(ws), np.sum(ws ** 2)
+    mu = (xs * ws[None, :]).sum(axis=1) / V1
+    dl = xs - mu[:, None]
+    Sigma = (dl * ws[None, :]) @ dl.T / (V1 - V2 / V1)
+    Sigma = 0.5 * (Sigma + Sigma.T)
+    if np.any(np.isinf(Sigma)) or np.any(np.isnan(Sigma)):
+        return None
+    try:
+        np.linalg.cholesky(Sigma)
+    except np.linalg.LinAlgError:
+        return None
+    return mu, Sigma
+
+
+def amis_replay(xs, log_P, N, q0, init_q=None):
+    """Replays (amis::AMIS)(log_pi, q, fitter) (amis_method.jl:26-83) on GIVEN draws xs (d x N(T+1), iteration-major) and their
+    log_pi values: returns the proposals fitted at every iteration, Delta, log_Omega and the final weights of iterations 2..T+1."""
+    xs = np.asarray(xs, float); log_P = np.asarray(log_P, float)
+    T1 = xs.shape[1] // N
+    qs = [tuple(np.array(a, float) for a in q0) for _ in range(T1)]
+    if init_q is not None:
+        qs[0] = tuple(np.array(a, float) for a in init_q)
+    Delta = np.zeros(N * T1); log_O = np.zeros(N * T1)
+    sl = lambda t0, t1: slice(t0 * N, t1 * N)  # noqa: E731
+    Delta[sl(0, 1)] = np.exp(mvnormal_logpdf(*qs[0], xs[:, sl(0, 1)]))
+    log_O[sl(0, 1)] = log_P[sl(0, 1)] - np.log(Delta[sl(0, 1)])
+    for t in range(1, T1):
+        est = estimate_parameters(xs[:, sl(0, t)], get_weights(log_O[sl(0, t)]))
+        if est is not None:
+            qs[t] = est
+        for i in range(t + 1):
+            Delta[sl(t, t + 1)] += np.exp(mvnormal_logpdf(*qs[i], xs[:, sl(t, t + 1)]))
+        log_O[sl(t, t + 1)] = log_P[sl(t, t + 1)] - np.log(Delta[sl(t, t + 1)] / (t + 1))
+        for i in range(t):
+            Delta[sl(i, i + 1)] += np.exp(mvnormal_logpdf(*qs[t], xs[:, sl(i, i + 1)]))
+            log_O[sl(i, i + 1)] = log_P[sl(i, i + 1)] - np.log(Delta[sl(i, i + 1)] / (t + 1))
+    return qs, Delta, log_O, (get_weights(log_O[sl(1, T1)]) if T1 > 1 else None)
+
+
+def weighted_quantile(v, w, p):
+    """StatsBase.quantile(v, w::Weights, p) restated loop for loop (zero weights removed, sorted by value)."""
+    v = np.asarray(v, float); w = np.asarray(w, float)
+    wsum = float(np.sum(w))
+    vw = sorted((float(a), float(b)) for a, b in zip(v, w) if b != 0)
+    if any(math.isnan(a) for a in v):
+        return float("nan")
+    out = vw[-1][0]
+    Sk = Skold = 0.0; vk = vkold = 0.0; k = 0
+    w1 = vw[0][1]
+    h = p * (wsum - w1) + w1
+    while Sk <= h:
+        k += 1
+        if k > len(vw):
+            return out
+        Skold, vkold = Sk, vk
+        vk, wk = vw[k - 1]
+        Sk += wk
+    return vkold + (h - Skold) / (Sk - Skold) * (vk - vkold)
+
+
+def find_cutoff(vals, ws, q):
+    """confidence_set.jl:23-27 on precomputed target_pdf values"""
+    return weighted_quantile(vals, ws, 1.0 - q)
+
+
+def approx_cutoff_area(vals, ws, c):
+    """confidence_set.jl:51-56"""
+    ws = np.asarray(ws, float)
+    wn = np.exp(np.log(ws) - np.log(np.sum(ws)))
+    return float(np.sum(wn[np.asarray(vals) >= c]))
+
+
+def set_iou(in_A, in_B, prior_pdf_vals):
+    """confidence_set.jl:73-81"""
+    ws = 1.0 / np.asarray(prior_pdf_vals, float)
+    ws = ws / np.sum(ws)
+    a, b = np.asarray(in_A, bool), np.asarray(in_B, bool)
+    return float(np.sum(ws[a & b]) / np.sum(ws[a | b]))
