@@ -170,4 +170,47 @@ function calc_mmd_b200(kernel_id::Integer, lengthscales::Vector{Float64}, X::Mat
     return out[]
 end
 
+
+# ---- variance engine ----------------------------------------------------------------------------------------------
+"Select the kernel behind the variance half of mean_and_var: :fp64 (DMMA), :int8 (tcgen05 on error-free byte slices) or :auto."
+function set_variance_engine!(engine::Symbol=:auto; slices::Integer=0)
+    ctx = context()
+    code = engine === :fp64 ? 0 : engine === :int8 ? 1 : 2
+    check(ctx, ccall((:bosip_b200_set_variance_engine, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, code, slices))
+end
+
+# ---- AMIS inner loop (src/samplers/amis/amis_method.jl:46-78) -------------------------------------------------------
+# A drop-in `fit_distribution!` + weight update for NormalProposal: the sample matrix, log_P, Delta and log_Omega are ordinary Julia
+# arrays here (HOST); a maintainer who keeps them in CUDA memory passes DEVICE pointers instead.
+function BOSIP.estimate_parameters!(dist::BOSIP.NormalProposal, xs::Matrix{Float64}, log_ws::Vector{Float64}, ::Val{:b200})
+    ctx = context(); d = size(xs, 1)
+    mean = zeros(d); cov = zeros(d, d); sums = zeros(2)
+    check(ctx, ccall((:bosip_b200_weighted_moments, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        ctx.h, d, xs, log_ws, size(xs, 2), HOST, mean, cov, sums, C_NULL))
+    Σ = Symmetric(cov)
+    (any(isinf.(Σ)) || !isposdef(Σ)) && return dist.dist          # normal.jl:92-95: keep the previous proposal
+    dist.dist = MvNormal(mean, Σ)
+end
+"Δ .+= Σ_q pdf.(Ref(q), eachcol(xs)) for a vector of MvNormal proposals (amis_method.jl:66-68,73-74)."
+function mixture_pdf_sum!(Δ::Vector{Float64}, qs::Vector{<:MvNormal}, xs::Matrix{Float64})
+    ctx = context(); d = size(xs, 1); nq = length(qs)
+    mus = hcat(mean.(qs)...)
+    Ls = [cholesky(Symmetric(Matrix(cov(q)))).L for q in qs]
+    Linvs = cat((Matrix(inv(L)) for L in Ls)...; dims=3)
+    lognorm = [-sum(log.(diag(L))) - d / 2 * log(2π) for L in Ls]
+    check(ctx, ccall((:bosip_b200_mixture_pdf_sum, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Cint, Cint, Ptr{Cdouble}),
+        ctx.h, d, nq, mus, Linvs, lognorm, xs, size(xs, 2), HOST, 1, Δ))
+    return Δ
+end
+"resample(xs, ws, count) (src/sampling.jl:55-57)"
+function resample_b200(xs::Matrix{Float64}, ws::Vector{Float64}, count::Integer; seed::Integer=0)
+    ctx = context(); out = Matrix{Float64}(undef, size(xs, 1), count)
+    check(ctx, ccall((:bosip_b200_resample, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Int64, UInt64, Int64, Cint, Ptr{Cdouble}, Ptr{Int64}),
+        ctx.h, size(xs, 1), xs, ws, size(xs, 2), seed, count, HOST, out, C_NULL))
+    return out
+end
+
 end # module

@@ -38,7 +38,7 @@ def gp_case(name, M, reps=3, **kw):
     print(json.dumps(out), flush=True)
 
 
-which = sys.argv[1:] or ["C1", "C2", "C3", "C5", "C5p4", "MMD", "TV"]
+which = sys.argv[1:] or ["C1", "C2", "C3", "C5", "C5p4", "MMD", "TV", "AMIS"]
 if "C1" in which: gp_case("C1", 10201, reps=20)
 if "C2" in which: gp_case("C2", 10 ** 6)
 if "C3" in which: gp_case("C3", 148 * 128 * 16)
@@ -68,3 +68,23 @@ if "TV" in which:
         v = bb.calc_tv(lw, a, t, ctx)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         print(json.dumps({"config": "TV", "G": G, "tv": v, "s": dt, "algorithmic_GBps": 24 * G / dt * 1e-9, "frac_of_hbm_6451": 24 * G / dt * 1e-9 / 6451.2}), flush=True)
+if "AMIS" in which:
+    # AMIS on the C3 posterior mean: T = 10 iterations x N = 1e5 draws, everything resident in HBM
+    pr = bb.synth.make_problem("C3")
+    model = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma)
+    problem = bb.BosipProblem(pr.X, pr.Y, model, bb.NormalLikelihood(pr.z_obs, pr.std_obs), bb.ProductPrior(pr.prior_kind, pr.prior_params),
+                              bounds=(pr.lb, pr.ub), ctx=ctx)
+    log_pi = bb.log_posterior_mean(problem)
+    q0 = bb.NormalProposal(0.5 * (pr.lb + pr.ub), np.diag((pr.ub - pr.lb) / 5.0))
+    amis = bb.AMIS(T=10, N=100_000)
+    amis(log_pi, q0, bb.AnalyticalFitter(), seed=1, ctx=ctx)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    xs, ws = amis(log_pi, q0, bb.AnalyticalFitter(), seed=2, ctx=ctx)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    # share of log_pi (the fused posterior sweep) in it
+    t0 = time.perf_counter()
+    for _ in range(11):
+        log_pi(xs[:, :100_000])
+    torch.cuda.synchronize(); dt_pi = time.perf_counter() - t0
+    print(json.dumps({"config": "AMIS on C3 log_posterior_mean", "T": 10, "N": 100_000, "s": dt, "draws_per_s": 11 * 100_000 / dt,
+                      "log_pi_share": dt_pi / dt, "ess": float(1.0 / (ws ** 2).sum().item())}), flush=True)
