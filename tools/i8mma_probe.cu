@@ -250,15 +250,18 @@ static void run_pattern(int blocks, int iters, int S, int mode, int nmax) {
 
 // ---------------------------------------------------------------- compile-time MMA sequences (tight issue loop): cost model of tcgen05.mma kind::i8
 // PAT 0: the engine's S=7 k-step (256+192, 256+128, 256+64, 256, 192, 128, 64); 1: 7 x N=256; 2: 14 x N=128; 3: 28 x N=64;
-// 4: 9 x N=192 + 1 x 64; 5: S=7 k-step with every MMA on its own accumulator columns (no shared D)
+// 4: 9 x N=192 + 1 x 64; 5: S=7 k-step with all MMAs on D column 0; 6: pattern 0 with a tcgen05.commit after every slice row
+// of every 4th k-step (what the engine's A ring needs); 7: pattern 0 with a commit after every k-step only
 template <int PAT>
 __global__ void __launch_bounds__(128) seq_kernel(int iters) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t done;
+  __shared__ __align__(8) uint64_t sink[8];
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5;
   unsigned char* sA = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   unsigned char* sB = sA + 7 * 16384;
+  if (tid == 0) for (int i = 0; i < 8; ++i) mbar_init(&sink[i], 1);
   for (int i = tid; i < (7 * 16384 + 7 * 8192) / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   if (tid == 0) { mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
@@ -274,16 +277,36 @@ __global__ void __launch_bounds__(128) seq_kernel(int iters) {
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     for (int it = 0; it < iters; ++it) {
       const uint32_t ko = (it & 3) * 32;
-      if (PAT == 0 || PAT == 5) {
+      if (PAT == 0 || PAT == 5 || PAT == 6 || PAT == 7) {
 #pragma unroll
         for (int a = 0; a < 7; ++a) {
           const uint64_t da = make_desc(a0 + a * 16384 + ko);
 #pragma unroll
           for (int c0 = a; c0 < 7; c0 += 4) {
             const int nb = (7 - c0) < 4 ? (7 - c0) : 4;
-            mma_i8(tb + (PAT == 0 ? 64 * (c0 - a) : 0), da, make_desc(b0 + c0 * 8192 + ko), make_idesc(128, 64 * nb), 1u);
+            mma_i8(tb + (PAT != 5 ? 64 * (c0 - a) : 0), da, make_desc(b0 + c0 * 8192 + ko), make_idesc(128, 64 * nb), 1u);
           }
+          if (PAT == 6 && (it & 3) == 3) mma_commit(&sink[a]);
         }
+        if (PAT == 7) mma_commit(&sink[7]);
+      } else if (PAT >= 8 && PAT <= 11) {
+        // the engine's real order: one iteration = one k-block = rows a = 6..0, each row its 4 k-steps, then a commit;
+        // PAT 8: commit per row + one per k-block (what vargemm_i8 does); 9: commit per 2 rows; 10: per 3 rows; 11: one per k-block
+        const int every = PAT == 8 ? 1 : PAT == 9 ? 2 : PAT == 10 ? 3 : 100;
+#pragma unroll
+        for (int a = 6; a >= 0; --a) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t da = make_desc(a0 + a * 16384 + ks * 32);
+#pragma unroll
+            for (int c0 = a; c0 < 7; c0 += 4) {
+              const int nb = (7 - c0) < 4 ? (7 - c0) : 4;
+              mma_i8(tb + 64 * (c0 - a), da, make_desc(b0 + c0 * 8192 + ks * 32), make_idesc(128, 64 * nb), 1u);
+            }
+          }
+          if ((6 - a) % every == every - 1) mma_commit(&sink[a]);
+        }
+        mma_commit(&sink[7]);
       } else if (PAT == 1) {
 #pragma unroll
         for (int a = 0; a < 7; ++a) mma_i8(tb + (a & 1) * 256, make_desc(a0 + a * 16384 + ko), make_desc(b0 + (a % 4) * 8192 + ko), make_idesc(128, 256), 1u);
@@ -321,7 +344,7 @@ static void run_seq(int blocks, int iters, const char* what) {
     CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
     float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
   }
-  printf("seq %d (%s): %.1f clk per k-step (1792 output columns; math floor 896)\n", PAT, what, best * 1e-3 * 1.965e9 / iters);
+  printf("seq %d (%s): %.1f clk per k-step (1792 output columns; math floor 896)\n", PAT, what, best * 1e-3 * 1.965e9 / iters / (PAT >= 8 ? 4 : 1));
 }
 
 int main(int argc, char** argv) {
@@ -339,6 +362,8 @@ int main(int argc, char** argv) {
   run_peak<256>(sms, 10000, 2);
   run_peak<64>(sms, 20000, 4);
   run_seq<0>(sms, 3000, "S=7 engine pattern"); run_seq<5>(sms, 3000, "same, all on D column 0"); run_seq<1>(sms, 3000, "7 x N=256");
+  run_seq<6>(sms, 3000, "S=7 pattern + commit per slice row every 4th k-step"); run_seq<7>(sms, 3000, "S=7 pattern + commit per k-step");
+  run_seq<8>(sms, 1000, "engine order, commit per row + per k-block"); run_seq<9>(sms, 1000, "engine order, commit per 2 rows"); run_seq<10>(sms, 1000, "engine order, commit per 3 rows"); run_seq<11>(sms, 1000, "engine order, one commit per k-block");
   run_seq<2>(sms, 3000, "14 x N=128"); run_seq<3>(sms, 3000, "28 x N=64"); run_seq<4>(sms, 3000, "9 x N=192 + N=64");
   for (int n = 32; n <= 256; n += 32) run_pattern(sms, 4000, 4, 2, n);
   for (int S = 6; S <= 8; ++S) for (int mode = 0; mode < 2; ++mode) run_pattern(sms, 2000, S, mode, 0);
