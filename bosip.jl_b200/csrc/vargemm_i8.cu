@@ -16,6 +16,8 @@
 // contiguously in descending b, so up to four of them form ONE tcgen05.mma of N = 256 whose output columns are four
 // adjacent group accumulators.  Roles: warp 0 = TMA producer (cp.async.bulk, full/empty mbarriers), warp 1 = TMEM allocation
 // + the single MMA-issuing thread, warps 2..9 = epilogue (tcgen05.ld, FP64 assembly, row sums).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bosip {
@@ -24,15 +26,15 @@ constexpr int I8_BM = 128, I8_BN = 64, I8_BK = 128;
 constexpr int I8_A_TILE = I8_BM * I8_BK;  // 16 KB: [128 rows][128 B], SWIZZLE_128B image
 constexpr int I8_B_TILE = I8_BN * I8_BK;  //  8 KB: [ 64 rows][128 B], SWIZZLE_128B image
 constexpr int I8_THREADS = 352;   // warp 0 TMA producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
-constexpr int I8_ISSUERS = 2;
+constexpr int I8_ISSUERS = 2;      // MMA-issuing threads of the default kernel; NI = 1 is kept as a cross-check (BOSIP_B200_I8_ISSUERS=1)
 constexpr int I8_EPI_WARPS = 8;
 
 template <int S> struct I8Cfg {
   // which of the two MMA threads issues slice a (a row of the slice-pair triangle); balanced in MMA count per k-step.
   // (A third issuing thread brought nothing at S = 7 and dead-locked at S = 8 on the GPU although the barrier protocol
   // completes in simulation; two threads are what has been validated.)
-  static constexpr int owner(int a) {
-    return (S == 6) ? ((a == 0 || a == 3 || a == 4) ? 0 : 1)
+  static constexpr int owner(int a, int ni) {
+    return ni == 1 ? 0 : (S == 6) ? ((a == 0 || a == 3 || a == 4) ? 0 : 1)
          : (S == 7) ? ((a == 0 || a == 3 || a == 5 || a == 6) ? 0 : 1)
                     : ((a == 0 || a == 3 || a == 4 || a == 7) ? 0 : 1);
   }
@@ -148,7 +150,7 @@ struct I8Args {
 // One MMA-issuing thread.  A single thread sustains ~100 clk per tcgen05.mma (descriptor arithmetic, uniform-register moves,
 // barrier polls), more than the small slice MMAs take to execute, so the slice rows of a k-block are dealt to two threads.
 // Integer accumulation is order-independent and the accumulators are handed over zeroed, so the streams need no ordering.
-template <int S, int Q>
+template <int S, int Q, int NI>
 __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_t sB_u, uint32_t tmem, uint64_t* a_full, uint64_t* a_empty,
                                          uint64_t* b_full, uint64_t* b_empty, uint64_t* t_full, uint64_t* t_empty) {
   using Cfg = I8Cfg<S>;
@@ -169,7 +171,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
         int waited = S;  // groups >= waited have been claimed by this thread for this tile
 #pragma unroll
         for (int a = S - 1; a >= 0; --a) {
-          if (Cfg::owner(a) != Q) continue;
+          if (Cfg::owner(a, NI) != Q) continue;
           // slice a meets groups a .. S-1.  The epilogue hands every group back zeroed, so all MMAs accumulate and the next
           // tile starts on the low-order groups while the previous one is still draining the high-order ones.
           if (kb == 0) {
@@ -210,7 +212,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
   }
 }
 
-template <int S>
+template <int S, int NI>
 __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args g) {
   using Cfg = I8Cfg<S>;
   extern __shared__ unsigned char smem_raw[];
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
 
   if (tid == 0) {
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], I8_ISSUERS); }
-    mbar_init(t_full, I8_ISSUERS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI); }
+    mbar_init(t_full, NI);
     for (int i = 0; i < S; ++i) mbar_init(&t_empty[i], I8_EPI_WARPS);
     mbar_fence_init();
   }
@@ -290,8 +292,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   } else if (warp == 1 || warp == 10) {
     // ================================================================ MMA issuers (one thread each, disjoint slice rows)
     if (lane == 0) {
-      if (warp == 1) i8_issue<S, 0>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
-      else i8_issue<S, 1>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      if (warp == 1) i8_issue<S, 0, NI>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      else if (NI > 1) i8_issue<S, 1, NI>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
     }
   } else {
     // ================================================================ epilogue: 8 warps, thread = (row, 32-column half)
@@ -468,11 +470,11 @@ int i8_nsub(const Gp* gp) {
   return nsub < 1 ? 1 : (nsub > 8 ? 8 : nsub);
 }
 
-template <int S>
-static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
-  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
+template <int S, int NI>
+static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
   const int grid = a.n_items < ctx->sms ? a.n_items : ctx->sms;
-  vargemm_i8_kernel<S><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
+  vargemm_i8_kernel<S, NI><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
   {
@@ -485,6 +487,14 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   }
 #endif
   return 0;
+}
+
+template <int S>
+static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
+  // two issuing threads accumulate into the same TMEM columns; exact integer arithmetic makes the result independent of their
+  // interleaving (tests/test_gpu_int8_engine.py checks the two variants bit for bit)
+  static const bool single = getenv("BOSIP_B200_I8_ISSUERS") && atoi(getenv("BOSIP_B200_I8_ISSUERS")) == 1;
+  return single ? launch_i8n<S, 1>(ctx, a, st) : launch_i8n<S, I8_ISSUERS>(ctx, a, st);
 }
 
 // Ks8: [p][mc/128][KB][S][16 KB]; q_part: [nsub][p][mc] scratch; q: [p][mc]

@@ -137,3 +137,30 @@ def test_int8_bi_ensemble_matches_fp64(bb, ctx, engine):
     fin = np.isfinite(a) & np.isfinite(b)
     assert np.sum(np.isfinite(a) != np.isfinite(b)) <= 4
     assert np.all(np.abs(a[fin] - b[fin]) <= TOL * np.abs(a[fin]) + 1e-7)
+
+
+def test_two_mma_issuers_equal_one_bit_for_bit(bb, ctx, engine, tmp_path):
+    """The default kernel deals the slice rows of a k-block to two MMA-issuing threads that accumulate into the same TMEM columns;
+    integer accumulation makes the result independent of how the two streams interleave.  BOSIP_B200_I8_ISSUERS=1 (read at first use,
+    hence the subprocess) selects the single-issuer kernel: the variances must agree to the last bit."""
+    import os
+    import subprocess
+    import sys
+    pr, model, ofit, Xq = _problem(bb, "C3", 6000)
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    engine("int8", 7)
+    _, var2 = post.mean_and_var(Xq)
+    out = tmp_path / "var1.npy"
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {repr(os.path.abspath(os.path.join(os.path.dirname(__file__), '..')))})\n"
+        "sys.path.insert(0, sys.path[0] + '/tests')\n"
+        "import bosip_b200 as bb\n"
+        "from test_gpu_int8_engine import _problem\n"
+        "ctx = bb.Context(0); ctx.set_variance_engine('int8', 7)\n"
+        "pr, model, ofit, Xq = _problem(bb, 'C3', 6000)\n"
+        "post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)\n"
+        f"np.save({repr(str(out))}, post.mean_and_var(Xq)[1])\n")
+    env = dict(os.environ, BOSIP_B200_I8_ISSUERS="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    assert np.array_equal(np.load(out), var2)
