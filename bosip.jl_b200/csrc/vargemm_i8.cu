@@ -30,15 +30,20 @@ constexpr int I8_ISSUERS = 2;      // MMA-issuing threads of the default kernel;
 constexpr int I8_EPI_WARPS = 8;
 
 template <int S> struct I8Cfg {
-  // which of the two MMA threads issues slice a (a row of the slice-pair triangle); balanced in MMA count per k-step.
-  // (A third issuing thread brought nothing at S = 7 and dead-locked at S = 8 on the GPU although the barrier protocol
-  // completes in simulation; two threads are what has been validated.)
+  // which of the two MMA threads issues slice a (a row of the slice-pair triangle); balanced in MMA count per k-step
   static constexpr int owner(int a, int ni) {
     return ni == 1 ? 0 : (S == 6) ? ((a == 0 || a == 3 || a == 4) ? 0 : 1)
          : (S == 7) ? ((a == 0 || a == 3 || a == 5 || a == 6) ? 0 : 1)
                     : ((a == 0 || a == 3 || a == 4 || a == 7) ? 0 : 1);
   }
-  static constexpr int A_SLOTS = (S >= 8) ? 5 : 6;
+  // A tiles live in one ring PER issuing thread (ring(ni) slots each): every full/empty barrier then has exactly one producer and
+  // one consumer, which is what the one-bit phase parity of an mbarrier can express.  (With a shared ring a thread can poll the
+  // NEXT fill of a slot whose current fill -- owned by the other thread -- has not landed yet; the parity test then passes early.
+  // That race dead-locked builds with a shallow shared ring.)
+  // Sized so that A rings + two B sets fill the 227 KB of shared memory: S = 6: 4 + 4, S = 7: 4 + 3, S = 8: 3 + 3 tiles of 16 KB.
+  static constexpr int A_SLOTS = (S == 6) ? 8 : (S == 7) ? 7 : 6;
+  static constexpr int ring(int q, int ni) { return ni == 1 ? A_SLOTS : (q == 0 ? (A_SLOTS + 1) / 2 : A_SLOTS / 2); }
+  static constexpr int ring_base(int q, int ni) { return (ni == 1 || q == 0) ? 0 : (A_SLOTS + 1) / 2; }
   static constexpr int B_SET = S * I8_B_TILE;
   static constexpr size_t SMEM = 1024 + (size_t)A_SLOTS * I8_A_TILE + 2 * (size_t)B_SET + 256;
 };
@@ -108,14 +113,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {  // 32 lanes x 32 columns <- 0
   const uint32_t z = 0u;
   asm volatile(
@@ -154,7 +151,7 @@ template <int S, int Q, int NI>
 __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_t sB_u, uint32_t tmem, uint64_t* a_full, uint64_t* a_empty,
                                          uint64_t* b_full, uint64_t* b_empty, uint64_t* t_full, uint64_t* t_empty) {
   using Cfg = I8Cfg<S>;
-  uint32_t a_base = 0, b_cnt = 0, tile_cnt = 0;  // a_base: A tiles consumed before this k-block (all rows, both issuers)
+  uint32_t a_cnt = 0, b_cnt = 0, tile_cnt = 0;  // a_cnt: A tiles this thread has consumed
   const uint32_t a_lo0 = umma_desc_lo(sA_u), b_lo0 = umma_desc_lo(sB_u);
   for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
     const int sub = item % g.nsub;
@@ -182,9 +179,9 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
             waited = a;
             I8_ACC(Q * 4 + 1);
           }
-          const uint32_t cnt = a_base + (uint32_t)(S - 1 - a);
-          const uint32_t as = cnt % Cfg::A_SLOTS;
-          { I8_T0(); mbar_wait_b(&a_full[as], (cnt / Cfg::A_SLOTS) & 1, 20 + Q); I8_ACC(Q * 4 + 2); }
+          const uint32_t as = (uint32_t)Cfg::ring_base(Q, NI) + a_cnt % Cfg::ring(Q, NI);   // this thread's own ring
+          { I8_T0(); mbar_wait_b(&a_full[as], (a_cnt / Cfg::ring(Q, NI)) & 1, 20 + Q); I8_ACC(Q * 4 + 2); }
+          ++a_cnt;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t a_lo = a_lo0 + as * (uint32_t)(I8_A_TILE >> 4);
           I8_T0();
@@ -202,7 +199,6 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
           umma_commit(&a_empty[as]);
           I8_ACC(Q * 4 + 3);
         }
-        a_base += S;
         umma_commit(&b_empty[bs]);
         ++b_cnt;
       }
@@ -215,14 +211,15 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
 template <int S, int NI>
 __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args g) {
   using Cfg = I8Cfg<S>;
+  constexpr int A_SLOTS = Cfg::A_SLOTS;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = base;
-  unsigned char* sB = base + (size_t)Cfg::A_SLOTS * I8_A_TILE;
+  unsigned char* sB = base + (size_t)A_SLOTS * I8_A_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * (size_t)Cfg::B_SET);
   uint64_t* a_full = bars;                       // [A_SLOTS]
-  uint64_t* a_empty = bars + Cfg::A_SLOTS;       // [A_SLOTS]
-  uint64_t* b_full = bars + 2 * Cfg::A_SLOTS;    // [2]
+  uint64_t* a_empty = bars + A_SLOTS;       // [A_SLOTS]
+  uint64_t* b_full = bars + 2 * A_SLOTS;    // [2]
   uint64_t* b_empty = b_full + 2;                // [2]
   uint64_t* t_full = b_empty + 2;                // accumulators complete -> epilogue
   uint64_t* t_empty = t_full + 1;                // [S] group accumulator drained and zeroed -> MMA
@@ -235,7 +232,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
 #endif
 
   if (tid == 0) {
-    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI); }
     mbar_init(t_full, NI);
     for (int i = 0; i < S; ++i) mbar_init(&t_empty[i], I8_EPI_WARPS);
@@ -253,7 +250,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      uint32_t a_cnt = 0, b_cnt = 0;
+      uint32_t a_cnt[2] = {0, 0}, b_cnt = 0;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const int sub = item % g.nsub, grp = item / g.nsub, mt = grp % g.m_tiles, j = grp / g.m_tiles;
         const uint8_t* Aj = g.A + ((size_t)j * g.mtA + mt) * g.KB * S * I8_A_TILE;
@@ -275,15 +272,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
             const uint8_t* Ak = Aj + (size_t)kb * S * I8_A_TILE;
 #pragma unroll 1
             for (int a = S - 1; a >= 0; --a) {  // least significant slice first: it only touches the accumulators the epilogue frees first
-              const uint32_t as = a_cnt % Cfg::A_SLOTS;
-              mbar_wait_b(&a_empty[as], ((a_cnt / Cfg::A_SLOTS) & 1) ^ 1, 2);
+              const int q = Cfg::owner(a, NI);
+              const uint32_t rq = (uint32_t)Cfg::ring(q, NI);
+              const uint32_t as = (uint32_t)Cfg::ring_base(q, NI) + a_cnt[q] % rq;
+              mbar_wait_b(&a_empty[as], ((a_cnt[q] / rq) & 1) ^ 1, 2);
 #ifdef BOSIP_I8_DEBUG_NOLOAD
               mbar_arrive(&a_full[as]);
 #else
               mbar_expect_tx(&a_full[as], I8_A_TILE);
               bulk_g2s(sA + (size_t)as * I8_A_TILE, Ak + (size_t)a * I8_A_TILE, I8_A_TILE, &a_full[as]);
 #endif
-              ++a_cnt;
+              ++a_cnt[q];
             }
           }
         }
@@ -321,6 +320,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         { I8_T0(); mbar_wait_b(t_full, tile_cnt & 1, 30); if (tid == 64) I8_ACC(16); }
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         I8_T0();
+        const double* cst = csj + (size_t)t * I8_BN + 32 * half;
         // Horner from the least significant group (group gi lives at columns 64 (S-1-gi)); each group is zeroed and handed back
         // to the MMA thread as soon as it has been read
         double w[32];
@@ -337,7 +337,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           for (int c = 0; c < 32; ++c) w[c] = (gi == S - 1) ? i32_to_f64(v[c]) : fma(w[c], 0.00390625, i32_to_f64(v[c]));
         }
         ++tile_cnt;
-        const double* cst = csj + (size_t)t * I8_BN + 32 * half;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const double x = w[c] * __ldg(cst + c);
@@ -472,8 +471,8 @@ int i8_nsub(const Gp* gp) {
 
 template <int S, int NI>
 static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
-  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
   const int grid = a.n_items < ctx->sms ? a.n_items : ctx->sms;
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
   vargemm_i8_kernel<S, NI><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
