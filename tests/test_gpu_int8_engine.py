@@ -164,3 +164,25 @@ def test_two_mma_issuers_equal_one_bit_for_bit(bb, ctx, engine, tmp_path):
     env = dict(os.environ, BOSIP_B200_I8_ISSUERS="1")
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     assert np.array_equal(np.load(out), var2)
+
+
+@pytest.mark.parametrize("d,p,N,M,kernel_id", [(10, 1, 4096, 1500, 2), (4, 2, 2000, 1000, 1), (3, 3, 1025, 700, 0)])
+def test_int8_large_training_sets(bb, ctx, engine, d, p, N, M, kernel_id):
+    """Deep contractions (BASELINE config 5: N = 4096, d = 10) and sizes just past a tile edge: many k-blocks per n-tile, several
+    n-tile subsets per query tile, a ragged last tile."""
+    rng = np.random.default_rng(N + d)
+    X = rng.uniform(-5, 5, (d, N)); Y = rng.standard_normal((p, N))
+    lam = rng.uniform(1.5, 4, (d, p)); alpha = rng.uniform(0.5, 2, p); sigma = 0.05 * alpha
+    Xq = rng.uniform(-5, 5, (d, M))
+    Xq[:, :32] = X[:, :32]
+    model = bb.GaussianProcess(kernel_id, lam, alpha, sigma)
+    post = bb.model_posterior(model, X, Y, ctx=ctx)
+    ofit = orc.gp_fit(kernel_id, X, Y, lam, alpha, sigma)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    engine("int8", 7)
+    mu, var = post.mean_and_var(Xq)
+    engine("fp64")
+    _, var64 = post.mean_and_var(Xq)
+    kxx = alpha ** 2
+    assert _var_err(var, ovar, kxx) < TOL and _var_err(var, var64, kxx) < TOL
+    assert _var_err(var, ovar, kxx) < 4 * _var_err(var64, ovar, kxx) + 1e-12
