@@ -97,7 +97,7 @@ PROTOTYPES = {
     "bosip_b200_resample": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "bosip_b200_fp64_peak": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
-    "bosip_b200_math_selftest": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "bosip_b200_math_selftest": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "bosip_b200_timing_reset": (C.c_int, [C.c_void_p, C.c_int]),
     "bosip_b200_timing_get": (C.c_int, [C.c_void_p, c_double_p, c_int64_p]),
 }

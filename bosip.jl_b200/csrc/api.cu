@@ -867,10 +867,10 @@ int bosip_b200_fp64_peak(bosip_b200_ctx* h, double* dmma, double* dfma) {
   return fp64_peak(ctx, dmma, dfma);
 }
 
-int bosip_b200_math_selftest(bosip_b200_ctx* h, const double* x, int64_t n, double* ef, double* qf, double* er, double* qr) {
+int bosip_b200_math_selftest(bosip_b200_ctx* h, const double* x, int64_t n, int variant, double* ef, double* qf, double* er, double* qr) {
   API_LOCK(h);
   if (!x || !ef || !qf || !er || !qr) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null argument");
-  return math_selftest(ctx, x, n, ef, qf, er, qr);
+  return math_selftest(ctx, x, n, variant, ef, qf, er, qr);
 }
 
 int bosip_b200_timing_reset(bosip_b200_ctx* h, int enable) {

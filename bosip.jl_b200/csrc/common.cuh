@@ -210,6 +210,6 @@ int weighted_moments(Ctx* ctx, int d, const double* X, const double* lw, int64_t
 int resample(Ctx* ctx, int d, const double* X, const double* ws, int64_t m, uint64_t seed, int64_t count, int mem, double* out, int64_t* idx);
 // peaks.cu
 int fp64_peak(Ctx* ctx, double* dmma, double* dfma);
-int math_selftest(Ctx* ctx, const double* x, int64_t n, double* e_fast, double* q_fast, double* e_ref, double* q_ref);
+int math_selftest(Ctx* ctx, const double* x, int64_t n, int variant, double* e_fast, double* q_fast, double* e_ref, double* q_ref);
 
 }  // namespace bosip

@@ -57,4 +57,65 @@ __device__ __forceinline__ double kernel_from_r2(double r2) {
   return (1.0 + s + r2 * (1.0 / 3.0)) * fast_exp_neg(s);           // Matern-5/2: (1 + sqrt5 r + 5 r^2/3) exp(-sqrt5 r)
 }
 
+
+// ------------------------------------------------------------------------------------------------ table-driven variants (cross-kernel)
+// exp(-s) = 2^m * T[j] * e^r with n = rint(-s * 64/ln2) = 64 m + j, T[j] = 2^(j/64) (correctly rounded), |r| <= ln2/128: a degree-5
+// polynomial is enough (truncation 3.5e-17), 10 FP64-pipe instructions instead of 16.  The table (512 B) lives in shared memory.
+__device__ const double EXP2_64TH[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, 0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0,
+    0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, 0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0, 0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0,
+    0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0, 0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0, 0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0,
+    0x1.6247eb03a5585p+0, 0x1.6623882552225p+0, 0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0, 0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0,
+    0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0, 0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0, 0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0,
+    0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, 0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
+__device__ __forceinline__ void load_exp_table(double* tab /* shared, 64 doubles */) {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = EXP2_64TH[i];
+}
+
+__device__ __forceinline__ double fast_exp_neg_t(double s, const double* __restrict__ tab) {
+  const double x = -s;
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double t = fma(x, 92.33248261689366, MAGIC);       // 64 / ln2
+  const double n = t - MAGIC;
+  double r = fma(n, -0x1.62e42fefa0000p-7, x);              // ln2/64, 36 significant bits: n * hi is exact for |n| < 2^17
+  r = fma(n, -2.572804622327669e-14, r);
+  double q = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);
+  q = fma(q, r, 1.6666666666666666e-01);
+  q = fma(q, r, 0.5);
+  const double p = fma(q, r * r, r);                        // e^r - 1
+  const int ni = __double2loint(t);                         // n as a two's-complement integer
+  const double T = tab[ni & 63];
+  const double v0 = fma(T, p, T);
+  const double v = __hiloint2double(__double2hiint(v0) + (int)((unsigned)(ni >> 6) << 20), __double2loint(v0));
+  return s > 708.0 ? 0.0 : v;
+}
+
+// sqrt with ONE coupled Newton step before the residual correction: the hardware seed is good to ~2^-22, one step gives 2^-44 and
+// the correction squares that again.
+__device__ __forceinline__ double fast_sqrt1(double x) {
+  const double xc = fmax(x, 1e-290);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xc));
+  double g = xc * y, h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  const double d = fma(-g, g, xc);
+  g = fma(d, h, g);
+  return x > 0.0 ? g : 0.0;
+}
+
+template <int KERNEL>
+__device__ __forceinline__ double kernel_from_r2_t(double r2, const double* __restrict__ tab) {
+  if (KERNEL == 0) return fast_exp_neg_t(r2, tab);
+  const double s = fast_sqrt1(r2);
+  if (KERNEL == 1) return (1.0 + s) * fast_exp_neg_t(s, tab);
+  return (1.0 + s + r2 * (1.0 / 3.0)) * fast_exp_neg_t(s, tab);
+}
+
 }  // namespace bosip

@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
   double* su = reinterpret_cast<double*>(smem_raw);          // [DP][nspan]
   double* sa = su + (size_t)DP * nspan;                       // [nspan]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ double exp_tab[64];
+  load_exp_table(exp_tab);
 
   const int j = blockIdx.z, split = blockIdx.y, p = gridDim.z;
   const int n0 = split * nspan;
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
         double kv[4];
         unsigned long long iv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2<KERNEL>(r2[e]); iv[e] = __double2ull_rn(kv[e] * fx); }
+        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2_t<KERNEL>(r2[e], exp_tab); iv[e] = __double2ull_rn(kv[e] * fx); }
         const double2 a01 = *reinterpret_cast<const double2*>(sa + n + 4 * q4);
         const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 4 * q4 + 2);
         acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
     }
     double kv[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) kv[e] = kernel_from_r2<KERNEL>(r2[e]);
+    for (int e = 0; e < 4; ++e) kv[e] = kernel_from_r2_t<KERNEL>(r2[e], exp_tab);
     const double2 a01 = *reinterpret_cast<const double2*>(sa + n);
     const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 2);
     acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);

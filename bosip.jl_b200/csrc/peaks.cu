@@ -64,23 +64,27 @@ int fp64_peak(Ctx* ctx, double* dmma, double* dfma) {
 }
 
 // self-test of fastmath.cuh against the CUDA library (host buffers)
-__global__ void math_selftest_kernel(const double* __restrict__ x, long long n, double* __restrict__ e_fast, double* __restrict__ q_fast,
-                                     double* __restrict__ e_ref, double* __restrict__ q_ref) {
+__global__ void math_selftest_kernel(const double* __restrict__ x, long long n, int variant, double* __restrict__ e_fast,
+                                     double* __restrict__ q_fast, double* __restrict__ e_ref, double* __restrict__ q_ref) {
+  __shared__ double tab[64];
+  load_exp_table(tab);
+  __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
-  e_fast[i] = fast_exp_neg(v); q_fast[i] = fast_sqrt(v);
+  if (variant == 0) { e_fast[i] = fast_exp_neg(v); q_fast[i] = fast_sqrt(v); }
+  else { e_fast[i] = fast_exp_neg_t(v, tab); q_fast[i] = fast_sqrt1(v); }
   e_ref[i] = exp(-v); q_ref[i] = sqrt(v);
 }
 
-int math_selftest(Ctx* ctx, const double* x, int64_t n, double* e_fast, double* q_fast, double* e_ref, double* q_ref) {
+int math_selftest(Ctx* ctx, const double* x, int64_t n, int variant, double* e_fast, double* q_fast, double* e_ref, double* q_ref) {
   if (n <= 0) return 0;
   cudaStream_t st = ctx->s_comp;
   double* d = nullptr;
   BOSIP_CUDA(ctx, cudaMalloc(&d, (size_t)n * 5 * 8));
   cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * 8, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, (long long)n, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
+    math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, (long long)n, variant, d + n, d + 2 * n, d + 3 * n, d + 4 * n);
     double* outs[4] = {e_fast, q_fast, e_ref, q_ref};
     for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaMemcpyAsync(outs[k], d + (size_t)(k + 1) * n, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -292,8 +292,9 @@ int bosip_b200_tv(bosip_b200_ctx* ctx, const double* log_ws, const double* a, co
  * denominators MEASURED_PEAKS.json lacks. */
 int bosip_b200_fp64_peak(bosip_b200_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
 /* Self-test of the library's branch-free FP64 exp(-x)/sqrt(x) (csrc/fastmath.cuh) against the CUDA library versions on
- * n host values x >= 0: four host outputs of n doubles each. */
-int bosip_b200_math_selftest(bosip_b200_ctx* ctx, const double* x, int64_t n, double* exp_neg_fast, double* sqrt_fast,
+ * n host values x >= 0: four host outputs of n doubles each.  variant 0: polynomial exp + two-step sqrt (MMD, TV, K build);
+ * variant 1: table-driven exp + one-step sqrt (cross-kernel). */
+int bosip_b200_math_selftest(bosip_b200_ctx* ctx, const double* x, int64_t n, int variant, double* exp_neg_fast, double* sqrt_fast,
                              double* exp_neg_ref, double* sqrt_ref);
 /* Per-kernel device time (CUDA events on the launching stream) accumulated since the last reset:
  * ms_out[0]=cross-kernel+mean, [1]=variance GEMM, [2]=epilogue/argmax, launches_out[0..2] the launch counts. */

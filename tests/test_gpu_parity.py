@@ -278,15 +278,17 @@ def test_error_behaviour(bb, ctx):
     assert post.mean(np.zeros((2, 0))).shape == (1, 0)
 
 
-def test_fast_math_accuracy(bb, ctx):
-    """csrc/fastmath.cuh (branch-free exp(-x), sqrt(x)) vs the CUDA library and vs NumPy: <= 2 ulp, exact at the edges."""
+@pytest.mark.parametrize("variant", [0, 1])
+def test_fast_math_accuracy(bb, ctx, variant):
+    """csrc/fastmath.cuh (branch-free exp(-x), sqrt(x); variant 1 = the cross-kernel's table-driven exp and one-step sqrt) vs the
+    CUDA library and vs NumPy: <= 2 ulp, exact at the edges."""
     rng = np.random.default_rng(0)
     x = np.concatenate([[0.0, 1e-300, 1e-200, 1e-30, 1e-16, 0.5, 1.0, 2.0, 707.9, 708.0, 708.1, 745.0, 1e3, 1e6],
                         rng.uniform(0, 50, 200000), 10.0 ** rng.uniform(-12, 2.8, 200000)])
     n = x.size
     outs = [np.empty(n) for _ in range(4)]
     dp = bb._lib.c_double_p
-    ctx._check(ctx.lib.bosip_b200_math_selftest(ctx.h, x.ctypes.data_as(dp), n, *[o.ctypes.data_as(dp) for o in outs]))
+    ctx._check(ctx.lib.bosip_b200_math_selftest(ctx.h, x.ctypes.data_as(dp), n, variant, *[o.ctypes.data_as(dp) for o in outs]))
     ef, qf, er, qr = outs
     big = x <= 700.0
     assert np.max(np.abs(ef[big] - er[big]) / er[big]) < 4.5e-16
