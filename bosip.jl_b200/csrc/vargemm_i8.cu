@@ -68,7 +68,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a protocol error traps (-> cudaErrorLaunchFailure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int tag = 0) {
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
@@ -127,11 +127,14 @@ __device__ __forceinline__ double i32_to_f64(uint32_t v) {  // exact: 2^52 + 2^3
 // ------------------------------------------------------------------------------------------------ the GEMM
 #ifdef BOSIP_I8_PROFILE  // dev build: cycles block 0 spends waiting vs issuing, printed by the host after every launch
 __device__ unsigned long long i8_dbg[32];
-#define I8_T0() const long long t0__ = clock64()
-#define I8_ACC(slot) do { if (blockIdx.x == 0) i8_dbg[slot] += (unsigned long long)(clock64() - t0__); } while (0)
+__device__ long long i8_ts[12][512];   // per-tile timestamps of block 0 (plain stores: cheap)
+#define I8_T0() do {} while (0)
+#define I8_ACC(slot) do {} while (0)
+#define I8_TS(ev, tile) do { if (blockIdx.x == 0 && (tile) < 512) i8_ts[ev][tile] = clock64(); } while (0)
 #else
 #define I8_T0() do {} while (0)
 #define I8_ACC(slot) do {} while (0)
+#define I8_TS(ev, tile) do {} while (0)
 #endif
 struct I8Args {
   const uint8_t* A;       // [p][mtA][KB][S][16 KB]     K* slices (kstar.cu, i8 mode)
@@ -176,6 +179,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
 #pragma unroll
             for (int gi = S - 1; gi >= 0; --gi)
               if (gi >= a && gi < waited) mbar_wait_b(&t_empty[gi], tile_cnt & 1, 100 + 10 * Q + gi);
+            if (waited == S) I8_TS(10 + Q, tile_cnt);   // first group wait of the tile satisfied
             waited = a;
             I8_ACC(Q * 4 + 1);
           }
@@ -184,7 +188,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
           ++a_cnt;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t a_lo = a_lo0 + as * (uint32_t)(I8_A_TILE >> 4);
-          I8_T0();
+          if (kb == 0 && waited == ((Q == 0) ? S - 1 : S - 3)) I8_TS(4 + Q, tile_cnt);   // this thread's first row of the tile is about to be issued
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             if (ks < nks) {
@@ -201,8 +205,10 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
         }
         umma_commit(&b_empty[bs]);
         ++b_cnt;
+        if (kb == 0) I8_TS(6 + Q, tile_cnt);   // first k-block of the tile issued
       }
       umma_commit(t_full);
+      I8_TS(0 + Q, tile_cnt);                  // whole tile issued
       ++tile_cnt;
     }
   }
@@ -317,12 +323,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
       double rs = 0.0;
       for (int t = g.T64 - 1; t >= 0; --t) {
         if (i8_subset(t, g.T64, g.nsub) != sub) continue;
-        { I8_T0(); mbar_wait_b(t_full, tile_cnt & 1, 30); if (tid == 64) I8_ACC(16); }
+        mbar_wait_b(t_full, tile_cnt & 1, 30);
+        if (tid == 64) I8_TS(2, tile_cnt);       // accumulators complete
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         I8_T0();
-        const double* cst = csj + (size_t)t * I8_BN + 32 * half;
+        // column scales of this thread's 32 columns: lane l fetches column l now (the load latency hides behind the Horner chain)
+        // and the values are handed round by shuffles at the end -- 32 dependent global loads per thread took ~13 000 clk per tile
+        const double my_cs = __ldg(csj + (size_t)t * I8_BN + 32 * half + lane);
         // Horner from the least significant group (group gi lives at columns 64 (S-1-gi)); each group is zeroed and handed back
-        // to the MMA thread as soon as it has been read
+        // to the MMA threads as soon as it has been read
         double w[32];
         uint32_t v[32];
 #pragma unroll
@@ -333,16 +342,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[gi]);
+          if (tid == 64 && gi == S - 1) I8_TS(3, tile_cnt);
+          if (tid == 64 && gi == 0) I8_TS(8, tile_cnt);
 #pragma unroll
           for (int c = 0; c < 32; ++c) w[c] = (gi == S - 1) ? i32_to_f64(v[c]) : fma(w[c], 0.00390625, i32_to_f64(v[c]));
         }
         ++tile_cnt;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const double x = w[c] * __ldg(cst + c);
+          const double x = w[c] * __shfl_sync(0xffffffffu, my_cs, c);
           rs = fma(x, x, rs);
         }
-        if (tid == 64) I8_ACC(17);
+        if (tid == 64) I8_TS(9, tile_cnt - 1);   // epilogue of the tile finished
       }
       // combine the two column halves of a row in a fixed order, one partial per work item
       if (half == 1) half_sum[row] = rs;
@@ -477,12 +488,34 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
   {
-    unsigned long long h[32], z[32] = {0};
+    static long long ts[12][512];
     cudaStreamSynchronize(st);
-    cudaMemcpyFromSymbol(h, i8_dbg, sizeof(h));
-    cudaMemcpyToSymbol(i8_dbg, z, sizeof(z));
-    fprintf(stderr, "[i8 profile, block 0, cycles] total %llu | issuer0: b_full %llu t_empty %llu a_full %llu issue+commit %llu | issuer1: %llu %llu %llu %llu | epilogue(thread 64): wait t_full %llu work %llu\n",
-            h[24], h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[16], h[17]);
+    cudaMemcpyFromSymbol(ts, i8_ts, sizeof(ts));
+    const int nt = 200;   // tiles 1 .. nt of block 0
+    double d[12] = {0};
+    for (int t = 1; t <= nt; ++t) {
+      const long long issued = std::max(ts[0][t - 1], ts[1][t - 1]);       // previous tile fully issued
+      d[0] += (double)(ts[2][t - 1] - issued);                             // -> its accumulators complete (pipe drain)
+      d[1] += (double)(ts[3][t - 1] - ts[2][t - 1]);                       // -> first group released
+      d[2] += (double)(ts[8][t - 1] - ts[2][t - 1]);                       // -> last group released
+      d[3] += (double)(std::min(ts[4][t], ts[5][t]) - ts[2][t - 1]);       // -> first MMA of the next tile issued
+      d[4] += (double)(std::max(ts[6][t], ts[7][t]) - ts[2][t - 1]);       // -> first k-block of the next tile issued
+      d[5] += (double)(std::max(ts[0][t], ts[1][t]) - std::max(ts[0][t - 1], ts[1][t - 1]));   // tile period
+      d[6] += (double)(ts[9][t - 1] - ts[2][t - 1]);                       // epilogue duration
+      d[7] += (double)(ts[10][t] - ts[3][t - 1]);                          // first release -> issuer 0 past its group wait
+      d[8] += (double)(ts[4][t] - ts[10][t]);                              // -> issuer 0 past its A-tile wait
+      d[9] += (double)(ts[9][t - 1] - ts[8][t - 1]);                       // last release -> epilogue of the tile finished
+    }
+    fprintf(stderr, "[i8 timeline, block 0, mean clk over %d tiles] issue-done->acc-complete %.0f | acc-complete->first release %.0f, ->last release %.0f, "
+                    "->next tile first MMA %.0f, ->next tile first k-block issued %.0f | epilogue %.0f | tile period %.0f | first release->issuer0 woke %.0f, then A-tile wait %.0f | last release->epilogue end %.0f\n",
+            nt, d[0] / nt, d[1] / nt, d[2] / nt, d[3] / nt, d[4] / nt, d[6] / nt, d[5] / nt, d[7] / nt, d[8] / nt, d[9] / nt);
+    {
+      long long lo = 1ll << 60, hi = 0; int slow = 0;
+      for (int t = 0; t < nt; ++t) { const long long e = ts[9][t] - ts[8][t]; lo = std::min(lo, e); hi = std::max(hi, e); slow += e > 2000; }
+      fprintf(stderr, "[i8 timeline] last release->epilogue end: min %lld max %lld, %d of %d tiles above 2000 clk; first tiles:", lo, hi, slow, nt);
+      for (int t = 0; t < 12; ++t) fprintf(stderr, " %lld", ts[9][t] - ts[8][t]);
+      fprintf(stderr, "\n");
+    }
   }
 #endif
   return 0;
@@ -543,7 +576,7 @@ __global__ void __launch_bounds__(128) i8_peak_kernel(int iters) {
                 umma_desc_sw128(smem_u32(sB + st * 256 * 128) + k * 32), umma_idesc_u8s8(128, 256), 1u);
     }
     umma_commit(&done);
-    mbar_wait_b(&done, 0);
+    mbar_wait_b(&done, 0, 0);
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
