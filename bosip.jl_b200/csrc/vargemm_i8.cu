@@ -127,7 +127,7 @@ __device__ __forceinline__ double i32_to_f64(uint32_t v) {  // exact: 2^52 + 2^3
 // ------------------------------------------------------------------------------------------------ the GEMM
 #ifdef BOSIP_I8_PROFILE  // dev build: cycles block 0 spends waiting vs issuing, printed by the host after every launch
 __device__ unsigned long long i8_dbg[32];
-__device__ long long i8_ts[12][512];   // per-tile timestamps of block 0 (plain stores: cheap)
+__device__ long long i8_ts[16][512];   // per-tile timestamps of block 0 (plain stores: cheap)
 #define I8_T0() do {} while (0)
 #define I8_ACC(slot) do {} while (0)
 #define I8_TS(ev, tile) do { if (blockIdx.x == 0 && (tile) < 512) i8_ts[ev][tile] = clock64(); } while (0)
@@ -330,30 +330,73 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         // column scales of this thread's 32 columns: lane l fetches column l now (the load latency hides behind the Horner chain)
         // and the values are handed round by shuffles at the end -- 32 dependent global loads per thread took ~13 000 clk per tile
         const double my_cs = __ldg(csj + (size_t)t * I8_BN + 32 * half + lane);
-        // Horner from the least significant group (group gi lives at columns 64 (S-1-gi)); each group is zeroed and handed back
-        // to the MMA threads as soon as it has been read
-        double w[32];
+        // sum_g 2^-8g D_g per column, least significant group first (group gi lives at columns 64 (S-1-gi)); each group is zeroed
+        // and handed back to the MMA threads as soon as it has been read.  FP64 instructions run ~17 x slower while the tensor
+        // pipe is busy (tools/i8mma_probe contend: DFMA 2.2 -> 36 clk per warp instruction; IMAD.WIDE, shifts, adds unaffected),
+        // and this code overlaps the next tile's MMAs.  So for S <= 7 the assembly is integer: the four low-order groups are summed
+        // exactly in an int64 (< 2^56) and rounded to units of 2^8 (2^7 low-order units at most, the scheme's own truncation is
+        // ~2^12 of them), the next two groups land on top at bits 24 and 32 (< 2^61); at S = 7 the most significant group stays in
+        // `v` and joins in FP64.  Four FP64-pipe instructions and one conversion per column are left instead of fifteen.
         uint32_t v[32];
+        if constexpr (S <= 7) {
+          long long acc[32];
 #pragma unroll
-        for (int gi = S - 1; gi >= 0; --gi) {
-          const uint32_t ta = taddr + (uint32_t)(64 * (S - 1 - gi));
-          tmem_ld32(ta, v);
-          tmem_zero32(ta);
-          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&t_empty[gi]);
-          if (tid == 64 && gi == S - 1) I8_TS(3, tile_cnt);
-          if (tid == 64 && gi == 0) I8_TS(8, tile_cnt);
+          for (int gi = S - 1; gi >= 0; --gi) {
+            const uint32_t ta = taddr + (uint32_t)(64 * (S - 1 - gi));
+            tmem_ld32(ta, v);
+            tmem_zero32(ta);
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[gi]);
+            if (tid == 64 && gi == S - 1) I8_TS(3, tile_cnt);
+            if (tid == 64 && gi == 0) I8_TS(8, tile_cnt);
+            if (tid == 96 && gi == 0) I8_TS(12, tile_cnt);   // the same on a sub-partition without an MMA-issuing thread
+            const int k = S - 1 - gi;
+            if (k <= 5) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) w[c] = (gi == S - 1) ? i32_to_f64(v[c]) : fma(w[c], 0.00390625, i32_to_f64(v[c]));
-        }
-        ++tile_cnt;
+              for (int c = 0; c < 32; ++c) {
+                const long long d = (long long)(int)v[c];
+                if (k == 0) acc[c] = d;
+                else if (k <= 3) acc[c] += d * (long long)(1 << (8 * k));
+                else if (k == 4) acc[c] += d * (long long)(1 << 24);
+                else acc[c] += d << 32;
+                if (k == 3) acc[c] = (acc[c] + 128) >> 8;
+              }
+            }
+          }
+          // x = cs 2^-8(S-2) (acc + 2^40 D_0).  (Replacing the remaining FP64 instructions by conversions and integer exponent
+          // arithmetic was measured slower: I2F.F64 costs 12.5 clk per warp instruction.)
+          const double sc = my_cs * ldexp(1.0, -8 * (S - 2));
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const double x = w[c] * __shfl_sync(0xffffffffu, my_cs, c);
-          rs = fma(x, x, rs);
+          for (int c = 0; c < 32; ++c) {
+            double wv = __ll2double_rn(acc[c]);
+            if (S == 7) wv = fma(i32_to_f64(v[c]), 1099511627776.0, wv);   // most significant group, 2^40 units
+            const double x = wv * __shfl_sync(0xffffffffu, sc, c);
+            rs = fma(x, x, rs);
+          }
+          ++tile_cnt;
+        } else {
+          double w[32];
+#pragma unroll
+          for (int gi = S - 1; gi >= 0; --gi) {
+            const uint32_t ta = taddr + (uint32_t)(64 * (S - 1 - gi));
+            tmem_ld32(ta, v);
+            tmem_zero32(ta);
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[gi]);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) w[c] = (gi == S - 1) ? i32_to_f64(v[c]) : fma(w[c], 0.00390625, i32_to_f64(v[c]));
+          }
+          ++tile_cnt;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const double x = w[c] * __shfl_sync(0xffffffffu, my_cs, c);
+            rs = fma(x, x, rs);
+          }
         }
         if (tid == 64) I8_TS(9, tile_cnt - 1);   // epilogue of the tile finished
+        if (tid == 96) I8_TS(13, tile_cnt - 1);
       }
       // combine the two column halves of a row in a fixed order, one partial per work item
       if (half == 1) half_sum[row] = rs;
@@ -444,7 +487,8 @@ __global__ void i8_slice_linv_kernel(const double* __restrict__ Linv, const doub
 int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
   if (gp->i8_S == S && gp->LinvI8) return 0;
   if (S < 6 || S > 8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: slices must be 6, 7 or 8");
-  // int32 accumulator bound: up to S pairs per group, each |sum| <= K * 255 * 128
+  // int32 accumulator bound: up to S pairs per group, each |sum| <= K * 255 * 128 (this also keeps the epilogue's int64 assembly,
+  // which places the single-pair most significant group at bit 32, below 2^61)
   if ((double)gp->N * S * 255.0 * 128.0 >= 2147483647.0)
     BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: N too large for exact int32 accumulation");
   if (gp->LinvI8) { cudaFree(gp->LinvI8); gp->LinvI8 = nullptr; }
@@ -488,7 +532,7 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
   {
-    static long long ts[12][512];
+    static long long ts[16][512];
     cudaStreamSynchronize(st);
     cudaMemcpyFromSymbol(ts, i8_ts, sizeof(ts));
     const int nt = 200;   // tiles 1 .. nt of block 0
@@ -515,6 +559,9 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       fprintf(stderr, "[i8 timeline] last release->epilogue end: min %lld max %lld, %d of %d tiles above 2000 clk; first tiles:", lo, hi, slow, nt);
       for (int t = 0; t < 12; ++t) fprintf(stderr, " %lld", ts[9][t] - ts[8][t]);
       fprintf(stderr, "\n");
+      double m3 = 0; long long hi3 = 0;
+      for (int t = 0; t < nt; ++t) { const long long e = ts[13][t] - ts[12][t]; m3 += (double)e; hi3 = std::max(hi3, e); }
+      fprintf(stderr, "[i8 timeline] the same tail on warp 3 (no MMA-issuing thread on its sub-partition): mean %.0f max %lld\n", m3 / nt, hi3);
     }
   }
 #endif

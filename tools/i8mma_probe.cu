@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
@@ -347,7 +348,89 @@ static void run_seq(int blocks, int iters, const char* what) {
   printf("seq %d (%s): %.1f clk per k-step (1792 output columns; math floor 896)\n", PAT, what, best * 1e-3 * 1.965e9 / iters / (PAT >= 8 ? 4 : 1));
 }
 
+// ---------------------------------------------------------------- what other warps can do while the tensor pipe is busy
+// warp 0 lane 0 issues N=256 MMAs back to back (or nothing when mma_on == 0); warps 1..4 (one per SM sub-partition) each run `reps`
+// iterations of a 32-instruction dependent-free loop of one instruction type and report their cycles.
+template <int KIND>  // 0 DFMA, 1 FFMA, 2 IMAD (32-bit), 3 IMAD.WIDE, 4 SHFL, 5 LOP3/IADD3 mix, 6 LDS
+__global__ void __launch_bounds__(160) contend_kernel(int iters, int mma_on, int reps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_base;
+  __shared__ double sd[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* sA = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = sA + 4 * 16384;
+  for (int i = tid; i < (4 * 16384 + 4 * 256 * 128) / 4; i += 160) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
+  if (tid < 64) sd[tid] = tid;
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  if (tid == 0) { mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (warp == 0) {
+    if (lane == 0 && mma_on) {
+      for (int it = 0; it < iters; ++it) {
+        const int st = it & 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_i8(tb + (uint32_t)((it & 1) * 256), make_desc(smem_u32(sA + st * 16384) + k * 32), make_desc(smem_u32(sB + st * 256 * 128) + k * 32), make_idesc(128, 256), 1u);
+      }
+      mma_commit(&done);
+      mbar_wait(&done, 0, 6);
+    }
+  } else {
+    double d0 = lane, d1 = 1.5, d2 = 0.25, d3 = 3.0; float f0 = lane, f1 = 1.5f, f2 = 0.25f, f3 = 3.f;
+    int i0 = lane, i1 = 3, i2 = 5, i3 = 7; long long l0 = lane, l1 = 1, l2 = 2, l3 = 3;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (KIND == 0) { d0 = fma(d0, 1.0000001, 0.5); d1 = fma(d1, 1.0000001, 0.5); d2 = fma(d2, 1.0000001, 0.5); d3 = fma(d3, 1.0000001, 0.5); }
+        if (KIND == 1) { f0 = fmaf(f0, 1.0001f, 0.5f); f1 = fmaf(f1, 1.0001f, 0.5f); f2 = fmaf(f2, 1.0001f, 0.5f); f3 = fmaf(f3, 1.0001f, 0.5f); }
+        if (KIND == 2) { i0 = i0 * 3 + 1; i1 = i1 * 3 + 1; i2 = i2 * 3 + 1; i3 = i3 * 3 + 1; }
+        if (KIND == 3) { l0 = (long long)i0 * 257 + l0; l1 = (long long)i1 * 257 + l1; l2 = (long long)i2 * 257 + l2; l3 = (long long)i3 * 257 + l3; i0 ^= (int)l3; }
+        if (KIND == 4) { i0 = __shfl_sync(0xffffffffu, i0, (lane + 1) & 31); i1 = __shfl_sync(0xffffffffu, i1, (lane + 2) & 31); i2 = __shfl_sync(0xffffffffu, i2, (lane + 3) & 31); i3 = __shfl_sync(0xffffffffu, i3, (lane + 4) & 31); }
+        if (KIND == 5) { i0 = (i0 ^ i1) + i2; i1 = (i1 & i3) + i0; i2 = (i2 | i0) - i1; i3 = (i3 ^ i2) + 7; }
+        if (KIND == 6) { d0 += sd[(i0++) & 63]; d1 += sd[(i1++) & 63]; d2 += sd[(i2++) & 63]; d3 += sd[(i3++) & 63]; }
+        if (KIND == 7) { l0 += __double_as_longlong(__ll2double_rn(l0)) >> 40; l1 += __double_as_longlong(__ll2double_rn(l1)) >> 40; l2 += __double_as_longlong(__ll2double_rn(l2)) >> 40; l3 += __double_as_longlong(__ll2double_rn(l3)) >> 40; }
+        if (KIND == 8) { i0 += __double2hiint(__int2double_rn(i0)) >> 20; i1 += __double2hiint(__int2double_rn(i1)) >> 20; i2 += __double2hiint(__int2double_rn(i2)) >> 20; i3 += __double2hiint(__int2double_rn(i3)) >> 20; }
+      }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) out[warp - 1] = t1 - t0;
+    if (d0 + d1 + d2 + d3 + f0 + f1 + f2 + f3 + i0 + i1 + i2 + i3 + l0 + l1 + l2 + l3 == 12345.678) out[7] = 1;
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
+}
+
+template <int KIND>
+static void run_contend(const char* what) {
+  const size_t smem = 4 * 16384 + 4 * 256 * 128 + 1024;
+  CK(cudaFuncSetAttribute(contend_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long* d; CK(cudaMalloc(&d, 64)); long long h[2][8];
+  for (int on = 0; on < 2; ++on) {
+    CK(cudaMemset(d, 0, 64));
+    contend_kernel<KIND><<<1, 160, smem>>>(4000, on, 2000, d);   // 16000 MMAs of 134 clk cover the 2000 x 32 instructions of the other warps
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h[on], d, 64, cudaMemcpyDeviceToHost));
+  }
+  printf("contend %-9s: clk per instruction per warp, tensor idle %.2f %.2f %.2f %.2f | tensor busy %.2f %.2f %.2f %.2f  (warps on sub-partitions 1,2,3,0)\n", what,
+         h[0][0] / 64000.0, h[0][1] / 64000.0, h[0][2] / 64000.0, h[0][3] / 64000.0, h[1][0] / 64000.0, h[1][1] / 64000.0, h[1][2] / 64000.0, h[1][3] / 64000.0);
+  cudaFree(d);
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "contend")) {
+    run_contend<0>("DFMA"); run_contend<1>("FFMA"); run_contend<2>("IMAD"); run_contend<3>("IMAD.WIDE"); run_contend<4>("SHFL"); run_contend<5>("LOP/IADD"); run_contend<6>("LDS+DADD"); run_contend<7>("I2F.64.s64"); run_contend<8>("I2F.64.s32");
+    return 0;
+  }
   int rc = 0;
   rc |= run_check<128>(1);
   rc |= run_check<128>(3);
