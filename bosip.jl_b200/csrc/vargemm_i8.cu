@@ -127,14 +127,17 @@ __device__ __forceinline__ double i32_to_f64(uint32_t v) {  // exact: 2^52 + 2^3
 // ------------------------------------------------------------------------------------------------ the GEMM
 #ifdef BOSIP_I8_PROFILE  // dev build: cycles block 0 spends waiting vs issuing, printed by the host after every launch
 __device__ unsigned long long i8_dbg[32];
-__device__ long long i8_ts[16][512];   // per-tile timestamps of block 0 (plain stores: cheap)
+__device__ long long i8_ts[16][512];
+__device__ long long i8_tw[2][8][512];   // per epilogue warp: [0] past the t_full wait, [1] first group released   // per-tile timestamps of block 0 (plain stores: cheap)
 #define I8_T0() do {} while (0)
 #define I8_ACC(slot) do {} while (0)
 #define I8_TS(ev, tile) do { if (blockIdx.x == 0 && (tile) < 512) i8_ts[ev][tile] = clock64(); } while (0)
+#define I8_TW(ev, w, tile) do { if (blockIdx.x == 0 && (tile) < 512) i8_tw[ev][w][tile] = clock64(); } while (0)
 #else
 #define I8_T0() do {} while (0)
 #define I8_ACC(slot) do {} while (0)
 #define I8_TS(ev, tile) do {} while (0)
+#define I8_TW(ev, w, tile) do {} while (0)
 #endif
 struct I8Args {
   const uint8_t* A;       // [p][mtA][KB][S][16 KB]     K* slices (kstar.cu, i8 mode)
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         if (i8_subset(t, g.T64, g.nsub) != sub) continue;
         mbar_wait_b(t_full, tile_cnt & 1, 30);
         if (tid == 64) I8_TS(2, tile_cnt);       // accumulators complete
+        if (lane == 0) I8_TW(0, ew, tile_cnt);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         I8_T0();
         // column scales of this thread's 32 columns: lane l fetches column l now (the load latency hides behind the Horner chain)
@@ -349,6 +353,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[gi]);
             if (tid == 64 && gi == S - 1) I8_TS(3, tile_cnt);
+            if (lane == 0 && gi == S - 1) I8_TW(1, ew, tile_cnt);
             if (tid == 64 && gi == 0) I8_TS(8, tile_cnt);
             if (tid == 96 && gi == 0) I8_TS(12, tile_cnt);   // the same on a sub-partition without an MMA-issuing thread
             const int k = S - 1 - gi;
@@ -558,6 +563,18 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       for (int t = 0; t < nt; ++t) { const long long e = ts[9][t] - ts[8][t]; lo = std::min(lo, e); hi = std::max(hi, e); slow += e > 2000; }
       fprintf(stderr, "[i8 timeline] last release->epilogue end: min %lld max %lld, %d of %d tiles above 2000 clk; first tiles:", lo, hi, slow, nt);
       for (int t = 0; t < 12; ++t) fprintf(stderr, " %lld", ts[9][t] - ts[8][t]);
+      fprintf(stderr, "\n");
+      static long long tw[2][8][512];
+      cudaMemcpyFromSymbol(tw, i8_tw, sizeof(tw));
+      double sk0 = 0, sk1 = 0; double late[8] = {0};
+      for (int t = 1; t <= nt; ++t) {
+        long long lo0 = 1ll << 62, hi0 = 0, lo1 = 1ll << 62, hi1 = 0;
+        for (int w8 = 0; w8 < 8; ++w8) { lo0 = std::min(lo0, tw[0][w8][t]); hi0 = std::max(hi0, tw[0][w8][t]); lo1 = std::min(lo1, tw[1][w8][t]); hi1 = std::max(hi1, tw[1][w8][t]); }
+        sk0 += (double)(hi0 - lo0); sk1 += (double)(hi1 - lo1);
+        for (int w8 = 0; w8 < 8; ++w8) late[w8] += (double)(tw[1][w8][t] - lo1);
+      }
+      fprintf(stderr, "[i8 timeline] epilogue warps: spread of passing t_full %.0f clk, of the first release %.0f clk; mean lateness of the first release per warp:", sk0 / nt, sk1 / nt);
+      for (int w8 = 0; w8 < 8; ++w8) fprintf(stderr, " %.0f", late[w8] / nt);
       fprintf(stderr, "\n");
       double m3 = 0; long long hi3 = 0;
       for (int t = 0; t < nt; ++t) { const long long e = ts[13][t] - ts[12][t]; m3 += (double)e; hi3 = std::max(hi3, e); }
