@@ -525,8 +525,10 @@ int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
 
 int i8_nsub(const Gp* gp) {
   const int T64 = (gp->N + I8_BN - 1) / I8_BN;
-  int nsub = T64 / 4;
-  return nsub < 1 ? 1 : (nsub > 8 ? 8 : nsub);
+  static const int forced = getenv("BOSIP_I8_NSUB") ? atoi(getenv("BOSIP_I8_NSUB")) : 0;  // dev A/B switch
+  int nsub = forced > 0 ? forced : T64 / 4;
+  nsub = nsub < 1 ? 1 : (nsub > 8 ? 8 : nsub);
+  return nsub > T64 ? T64 : nsub;
 }
 
 template <int S, int NI>
