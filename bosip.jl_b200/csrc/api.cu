@@ -193,7 +193,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   // ---- variance engine (FP64 DMMA or INT8 tcgen05 with error-free slicing)
   // AUTO: the INT8 engine pays off once the contraction is more than a tile deep; below that the FP64 kernel is as fast
   bool i8 = sw.need_var && (ctx->var_engine == BOSIP_B200_VAR_INT8 || (ctx->var_engine == BOSIP_B200_VAR_AUTO && gp->N >= 128));
-  if (i8 && ctx->var_engine == BOSIP_B200_VAR_AUTO && (double)gp->N * ctx->var_slices * 255.0 * 128.0 >= 2147483647.0) i8 = false;
+  if (i8 && ctx->var_engine == BOSIP_B200_VAR_AUTO && ((double)gp->N * ctx->var_slices * 255.0 * 128.0 >= 2147483647.0 || gp->N >= 8192)) i8 = false;
   const int S8 = ctx->var_slices, KB8 = (gp->N + 127) / 128;
   int nsub8 = 1;
   if (i8) {

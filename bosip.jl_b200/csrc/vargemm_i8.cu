@@ -336,13 +336,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         const double my_cs = __ldg(csj + (size_t)t * I8_BN + 32 * half + lane);
         // sum_g 2^-8g D_g per column, least significant group first (group gi lives at columns 64 (S-1-gi)); each group is zeroed
         // and handed back to the MMA threads as soon as it has been read.  FP64 instructions run ~17 x slower while the tensor
-        // pipe is busy (tools/i8mma_probe contend: DFMA 2.2 -> 36 clk per warp instruction; IMAD.WIDE, shifts, adds unaffected),
-        // and this code overlaps the next tile's MMAs.  So for S <= 7 the assembly is integer: the four low-order groups are summed
-        // exactly in an int64 (< 2^56) and rounded to units of 2^8 (2^7 low-order units at most, the scheme's own truncation is
-        // ~2^12 of them), the next two groups land on top at bits 24 and 32 (< 2^61); at S = 7 the most significant group stays in
-        // `v` and joins in FP64.  Four FP64-pipe instructions and one conversion per column are left instead of fifteen.
+        // pipe is busy (tools/i8mma_probe contend: DFMA 2.2 -> 36 clk per warp instruction; IMAD.WIDE, shifts, adds, I2F unaffected),
+        // and this code overlaps the next tile's MMAs.  So for S <= 7 the whole assembly is ONE int64 per column: the four low-order
+        // groups are summed exactly (< 2^56) and rounded to units of 2^R -- R = 11 at S = 7 (rms 590 low-order units against the
+        // ~630 of truncation the scheme has anyway: measured, errors grow 1.4 x), 8 at S = 6 -- and the remaining groups land on top at bits 8k - R; the single-
+        // pair most significant group (|D_0| <= K 2^13, K < 8192) ends below 2^63.  One conversion, one scale and one FMA per column remain.
         uint32_t v[32];
         if constexpr (S <= 7) {
+          constexpr int R = (S == 7) ? 11 : 8;
           long long acc[32];
 #pragma unroll
           for (int gi = S - 1; gi >= 0; --gi) {
@@ -357,26 +358,21 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
             if (tid == 64 && gi == 0) I8_TS(8, tile_cnt);
             if (tid == 96 && gi == 0) I8_TS(12, tile_cnt);   // the same on a sub-partition without an MMA-issuing thread
             const int k = S - 1 - gi;
-            if (k <= 5) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const long long d = (long long)(int)v[c];
-                if (k == 0) acc[c] = d;
-                else if (k <= 3) acc[c] += d * (long long)(1 << (8 * k));
-                else if (k == 4) acc[c] += d * (long long)(1 << 24);
-                else acc[c] += d << 32;
-                if (k == 3) acc[c] = (acc[c] + 128) >> 8;
-              }
+            for (int c = 0; c < 32; ++c) {
+              const long long d = (long long)(int)v[c];
+              if (k == 0) acc[c] = d;
+              else if (k <= 3) acc[c] += d * (long long)(1 << (8 * k));
+              else if (8 * k - R < 31) acc[c] += d * (long long)(1 << (8 * k - R));
+              else acc[c] += d << (8 * k - R);
+              if (k == 3) acc[c] = (acc[c] + (1ll << (R - 1))) >> R;
             }
           }
-          // x = cs 2^-8(S-2) (acc + 2^40 D_0).  (Replacing the remaining FP64 instructions by conversions and integer exponent
-          // arithmetic was measured slower: I2F.F64 costs 12.5 clk per warp instruction.)
-          const double sc = my_cs * ldexp(1.0, -8 * (S - 2));
+          const double sc = my_cs * ldexp(1.0, R - 8 * (S - 1));   // acc is in units of 2^R low-order units
+          // (scaling by integer exponent arithmetic instead of the DMUL was measured slower)
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            double wv = __ll2double_rn(acc[c]);
-            if (S == 7) wv = fma(i32_to_f64(v[c]), 1099511627776.0, wv);   // most significant group, 2^40 units
-            const double x = wv * __shfl_sync(0xffffffffu, sc, c);
+            const double x = __ll2double_rn(acc[c]) * __shfl_sync(0xffffffffu, sc, c);
             rs = fma(x, x, rs);
           }
           ++tile_cnt;
@@ -494,8 +490,8 @@ int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
   if (S < 6 || S > 8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: slices must be 6, 7 or 8");
   // int32 accumulator bound: up to S pairs per group, each |sum| <= K * 255 * 128 (this also keeps the epilogue's int64 assembly,
   // which places the single-pair most significant group at bit 32, below 2^61)
-  if ((double)gp->N * S * 255.0 * 128.0 >= 2147483647.0)
-    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: N too large for exact int32 accumulation");
+  if ((double)gp->N * S * 255.0 * 128.0 >= 2147483647.0 || gp->N >= 8192)
+    BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: N too large for exact integer accumulation (N < 8192)");
   if (gp->LinvI8) { cudaFree(gp->LinvI8); gp->LinvI8 = nullptr; }
   if (gp->cscale) { cudaFree(gp->cscale); gp->cscale = nullptr; }
   const int N = gp->N, p = gp->p;
