@@ -138,7 +138,8 @@ int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
  *   BOSIP_B200_VAR_INT8  tcgen05 INT8 tensor cores on error-free byte slices of both operands (Ozaki splitting):
  *                        `slices` bytes of fixed point per operand (6, 7 or 8; 0 = 7, i.e. 2^-56 of the row scale),
  *                        integer products exact, one FP64 rounding per Horner step in the epilogue.
- * Both satisfy the 1e-10 parity bound; results differ in the last bits. */
+ * Both satisfy the 1e-10 parity bound; results differ in the last bits.  The INT8 engine needs N < 8192 (exact integer
+ * accumulation); BOSIP_B200_VAR_AUTO falls back to FP64 above that, an explicit INT8 request returns BOSIP_B200_EINVAL. */
 #define BOSIP_B200_VAR_FP64 0
 #define BOSIP_B200_VAR_INT8 1
 #define BOSIP_B200_VAR_AUTO 2 /* default: INT8 for N >= 128 training points, FP64 below */
