@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libbosip_b200.so")
 SOURCES = ["api.cu", "kstar.cu", "vargemm.cu", "vargemm_i8.cu", "epilogue.cu", "fit.cu", "metrics.cu", "sampler.cu", "peaks.cu"]
-HEADERS = ["common.cuh", "philox.cuh", os.path.join("..", "..", "include", "bosip_b200.h")]
+HEADERS = ["common.cuh", "philox.cuh", "fastmath.cuh", os.path.join("..", "..", "include", "bosip_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -60,7 +60,10 @@ __device__ __forceinline__ double kernel_from_r2(double r2) {
 
 // ------------------------------------------------------------------------------------------------ table-driven variants (cross-kernel)
 // exp(-s) = 2^m * T[j] * e^r with n = rint(-s * 64/ln2) = 64 m + j, T[j] = 2^(j/64) (correctly rounded), |r| <= ln2/128: a degree-5
-// polynomial is enough (truncation 3.5e-17), 10 FP64-pipe instructions instead of 16.  The table (512 B) lives in shared memory.
+// polynomial is enough (truncation 3.5e-17).  9 FP64-pipe instructions instead of 16; the table (512 B) lives in shared memory.
+// The argument reduction uses ln2/64 rounded to double (off by 3.6e-19): the result carries a relative error of up to
+// 3.4e-17 * s on top of the usual ~1.5 ulp, i.e. an ABSOLUTE error <= 3.4e-17 * s * exp(-s) <= 1.3e-17.  Every consumer sums
+// kernel values against O(1) ones (K* rows, MMD means), so the absolute bound is the one that matters.
 __device__ const double EXP2_64TH[64] = {
     0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0, 0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0,
     0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0, 0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
@@ -74,48 +77,62 @@ __device__ const double EXP2_64TH[64] = {
     0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0, 0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
-__device__ __forceinline__ void load_exp_table(double* tab /* shared, 64 doubles */) {
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = EXP2_64TH[i];
+// Shared-memory copy of the table, each entry replicated REP times: lane l reads copy (l & (REP - 1)), which removes bank
+// conflicts between lanes (REP = 16: none).  Measured on B200 this buys nothing (cross-kernel 3.49 / 3.55 / 3.86 ms per 303 104 C3
+// points at REP = 1 / 8 / 16; the 8 KB copy costs the fourth resident CTA): these loops are bound by the issue port, which an
+// FP64 instruction holds for two cycles (time ~ 2 * FP64 + other instructions), not by shared-memory wavefronts.  So REP = 1.
+template <int REP>
+__device__ __forceinline__ void load_exp_table(double* tab /* shared, 64 * REP doubles */) {
+  for (int i = threadIdx.x; i < 64 * REP; i += blockDim.x) tab[i] = EXP2_64TH[i / REP];
 }
+template <int REP>
+__device__ __forceinline__ const double* exp_table_lane(const double* tab) { return tab + (threadIdx.x & (REP - 1)); }
 
+// tab: the calling lane's view of the table (exp_table_lane).  CUT = false skips the underflow cut-off: only for callers whose
+// argument is bounded well below 708.
+template <int REP, bool CUT = true>
 __device__ __forceinline__ double fast_exp_neg_t(double s, const double* __restrict__ tab) {
   const double x = -s;
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
   const double t = fma(x, 92.33248261689366, MAGIC);       // 64 / ln2
   const double n = t - MAGIC;
-  double r = fma(n, -0x1.62e42fefa0000p-7, x);              // ln2/64, 36 significant bits: n * hi is exact for |n| < 2^17
-  r = fma(n, -2.572804622327669e-14, r);
+  const double r = fma(n, -0x1.62e42fefa39efp-7, x);       // ln2/64
   double q = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);
   q = fma(q, r, 1.6666666666666666e-01);
   q = fma(q, r, 0.5);
   const double p = fma(q, r * r, r);                        // e^r - 1
   const int ni = __double2loint(t);                         // n as a two's-complement integer
-  const double T = tab[ni & 63];
+  const double T = tab[(ni & 63) * REP];
   const double v0 = fma(T, p, T);
-  const double v = __hiloint2double(__double2hiint(v0) + (int)((unsigned)(ni >> 6) << 20), __double2loint(v0));
-  return s > 708.0 ? 0.0 : v;
+  const int hi = __double2hiint(v0) + (int)((unsigned)(ni >> 6) << 20);
+  if (!CUT) return __hiloint2double(hi, __double2loint(v0));
+  // s in (708.06, +Inf] -> (almost) 0, decided on the high word in the integer pipe (negative s and NaN fall through).  Only the
+  // high word is cleared: the result is a denormal below 2^-1042 rather than an exact zero, one select instead of two.
+  const unsigned hs = (unsigned)__double2hiint(s);
+  return __hiloint2double((hs - 0x40862001u) <= (0x7ff00000u - 0x40862001u) ? 0 : hi, __double2loint(v0));
 }
 
-// sqrt with ONE coupled Newton step before the residual correction: the hardware seed is good to ~2^-22, one step gives 2^-44 and
-// the correction squares that again.
+// sqrt(x + 1e-300) for x >= 0 with ONE coupled Newton step before the residual correction: the hardware seed is good to ~2^-22,
+// one step gives 2^-44 and the correction squares that again.  The offset replaces the compare/select guards around x = 0
+// (rsqrt(0) = Inf): it is invisible for x >= 1e-284, and x = 0 gives 1e-150, which every kernel formula maps to k = 1 exactly.
 __device__ __forceinline__ double fast_sqrt1(double x) {
-  const double xc = fmax(x, 1e-290);
+  const double xc = x + 1e-300;
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xc));
-  double g = xc * y, h = 0.5 * y;
+  double g = xc * y;
+  double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));   // y / 2 (y is a normal number)
   const double r = fma(-h, g, 0.5);
   g = fma(g, r, g); h = fma(h, r, h);
   const double d = fma(-g, g, xc);
-  g = fma(d, h, g);
-  return x > 0.0 ? g : 0.0;
+  return fma(d, h, g);
 }
 
-template <int KERNEL>
+template <int KERNEL, int REP, bool CUT = true>
 __device__ __forceinline__ double kernel_from_r2_t(double r2, const double* __restrict__ tab) {
-  if (KERNEL == 0) return fast_exp_neg_t(r2, tab);
+  if (KERNEL == 0) return fast_exp_neg_t<REP, CUT>(r2, tab);
   const double s = fast_sqrt1(r2);
-  if (KERNEL == 1) return (1.0 + s) * fast_exp_neg_t(s, tab);
-  return (1.0 + s + r2 * (1.0 / 3.0)) * fast_exp_neg_t(s, tab);
+  if (KERNEL == 1) return (1.0 + s) * fast_exp_neg_t<REP, CUT>(s, tab);
+  return (1.0 + s + r2 * (1.0 / 3.0)) * fast_exp_neg_t<REP, CUT>(s, tab);
 }
 
 }  // namespace bosip

@@ -21,6 +21,10 @@ __device__ __forceinline__ void byte_transpose4(uint32_t x0, uint32_t x1, uint32
   o[2] = __byte_perm(b, e, 0x5410); o[3] = __byte_perm(b, e, 0x7632);
 }
 
+#ifndef KSTAR_EXP_REP
+#define KSTAR_EXP_REP 1   // copies of the exp table (fastmath.cuh: replication measured, no gain)
+#endif
+
 // MODE 0: mean only; 1: FP64 K* chunks (vargemm.cu); 2: S unsigned byte slices of round(k * 2^(8S-1)) written as
 // SWIZZLE_128B tile images [j][m-tile][k-block][slice][128 rows][128 B] for the INT8 engine (vargemm_i8.cu)
 template <int KERNEL, int DP, int MODE, int S>
@@ -33,8 +37,9 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
   double* su = reinterpret_cast<double*>(smem_raw);          // [DP][nspan]
   double* sa = su + (size_t)DP * nspan;                       // [nspan]
   __shared__ __align__(8) uint64_t bar;
-  __shared__ double exp_tab[64];
-  load_exp_table(exp_tab);
+  __shared__ double exp_tab_all[64 * KSTAR_EXP_REP];
+  load_exp_table<KSTAR_EXP_REP>(exp_tab_all);
+  const double* exp_tab = exp_table_lane<KSTAR_EXP_REP>(exp_tab_all);
 
   const int j = blockIdx.z, split = blockIdx.y, p = gridDim.z;
   const int n0 = split * nspan;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
         double kv[4];
         unsigned long long iv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2_t<KERNEL>(r2[e], exp_tab); iv[e] = __double2ull_rn(kv[e] * fx); }
+        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2_t<KERNEL, KSTAR_EXP_REP>(r2[e], exp_tab); iv[e] = __double2ull_rn(kv[e] * fx); }
         const double2 a01 = *reinterpret_cast<const double2*>(sa + n + 4 * q4);
         const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 4 * q4 + 2);
         acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
     }
     double kv[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) kv[e] = kernel_from_r2_t<KERNEL>(r2[e], exp_tab);
+    for (int e = 0; e < 4; ++e) kv[e] = kernel_from_r2_t<KERNEL, KSTAR_EXP_REP>(r2[e], exp_tab);
     const double2 a01 = *reinterpret_cast<const double2*>(sa + n);
     const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 2);
     acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);

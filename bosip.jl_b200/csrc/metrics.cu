@@ -12,58 +12,97 @@ namespace bosip {
 // sum_{i,j} k(P_i, Q_j) for a 128-row tile x a strip of column tiles.  Thread = row point (coordinates in registers),
 // column tile staged in shared memory (SoA) and read as broadcasts.  In symmetric mode (P == Q) only column tiles
 // >= row tile are visited, off-diagonal tiles weighted 2: the result is still the full V-statistic incl. diagonal.
+//
+// The kernel is FP64-pipe bound, so the instruction count per pair is what matters.  Points are stored centred and scaled
+// with their squared norm as an extra SoA row; when every norm is small (MMD_EXPAND_LIMIT) the squared distance is formed
+// as |p|^2 + |q|^2 - 2 p.q (d + 1 instructions, absolute error <= ~(d + 2) 2^-53 max|p|^2, i.e. <= 1e-13 relative in k)
+// instead of sum (p_k - q_k)^2 (2 d instructions).  Data that is spread over many length-scales takes the difference form;
+// the choice is made on the device from the maximum norm the scaling pass recorded, identically on every rank.
 constexpr int MMD_TILE = 128;
-constexpr int MMD_STRIP = 16;  // column tiles per CTA
+constexpr int MMD_STRIP = 16;            // column tiles per CTA
+constexpr int MMD_EXP_REP = 1;           // copies of the exp table in shared memory (fastmath.cuh: replication buys nothing)
+constexpr double MMD_EXPAND_LIMIT = 128.0;  // largest scaled squared norm for which the expanded distance is used
 
+template <int KERNEL, int DP, bool EXPAND>
+__device__ __forceinline__ double mmd_tile_sum(const double (&pi)[DP], double pn, const double (*sq)[MMD_TILE], int jmax,
+                                               const double* exp_tab) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int jj = 0;
+  for (; jj + 4 <= jmax; jj += 4) {
+    double r2[4];
+    if (EXPAND) {
+      const double2 n01 = *reinterpret_cast<const double2*>(&sq[DP][jj]);
+      const double2 n23 = *reinterpret_cast<const double2*>(&sq[DP][jj + 2]);
+      r2[0] = pn + n01.x; r2[1] = pn + n01.y; r2[2] = pn + n23.x; r2[3] = pn + n23.y;
+    } else {
+      r2[0] = r2[1] = r2[2] = r2[3] = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      const double2 q01 = *reinterpret_cast<const double2*>(&sq[k][jj]);
+      const double2 q23 = *reinterpret_cast<const double2*>(&sq[k][jj + 2]);
+      if (EXPAND) {   // pi holds -2 p
+        r2[0] = fma(pi[k], q01.x, r2[0]); r2[1] = fma(pi[k], q01.y, r2[1]); r2[2] = fma(pi[k], q23.x, r2[2]); r2[3] = fma(pi[k], q23.y, r2[3]);
+      } else {
+        const double t0 = pi[k] - q01.x, t1 = pi[k] - q01.y, t2 = pi[k] - q23.x, t3 = pi[k] - q23.y;
+        r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]); r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
+      }
+    }
+    // expanded form: r2 <= 4 * MMD_EXPAND_LIMIT, so exp cannot underflow (no cut-off); rounding can leave r2 a few ulps of
+    // the norms below 0, which the square root of the Matern kernels must not see
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += kernel_from_r2_t<KERNEL, MMD_EXP_REP, !EXPAND>((EXPAND && KERNEL != 0) ? fabs(r2[e]) : r2[e], exp_tab);
+  }
+  for (; jj < jmax; ++jj) {
+    double r2 = EXPAND ? pn + sq[DP][jj] : 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      if (EXPAND) r2 = fma(pi[k], sq[k][jj], r2);
+      else { const double t = pi[k] - sq[k][jj]; r2 = fma(t, t, r2); }
+    }
+    acc[0] += kernel_from_r2_t<KERNEL, MMD_EXP_REP, !EXPAND>((EXPAND && KERNEL != 0) ? fabs(r2) : r2, exp_tab);
+  }
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
 
-// Ps/Qs: scaled points, SoA [dp][np] / [dp][nq] (zero padded to multiples of 128 in count; padded points are masked)
+// Ps/Qs: centred, scaled points, SoA [dp + 1][np] / [dp + 1][nq] (row dp = squared norm; zero padded to multiples of 128
+// in count; padded points are masked).  norm_max_bits: bit pattern of the largest squared norm of either set.
 template <int KERNEL, int DP>
 __global__ void __launch_bounds__(MMD_TILE)
 mmd_kernel(const double* __restrict__ Ps, long long np, long long np_pad, const double* __restrict__ Qs, long long nq,
-           long long nq_pad, int symmetric, int rank, int world, double* __restrict__ partial) {
-  __shared__ __align__(16) double sq[DP][MMD_TILE];
+           long long nq_pad, int symmetric, int rank, int world, const unsigned long long* __restrict__ norm_max_bits,
+           double* __restrict__ partial) {
+  __shared__ __align__(16) double sq[DP + 1][MMD_TILE];
   __shared__ double red[MMD_TILE];
+  __shared__ double exp_tab_all[64 * MMD_EXP_REP];
+  load_exp_table<MMD_EXP_REP>(exp_tab_all);
+  const double* exp_tab = exp_table_lane<MMD_EXP_REP>(exp_tab_all);
   const long long cta = (long long)blockIdx.y * gridDim.x + blockIdx.x;
   const int rt = blockIdx.x;                    // row tile
   const int ct0 = blockIdx.y * MMD_STRIP;       // first column tile of the strip
   const int n_ct = (int)(nq_pad / MMD_TILE);
   double total = 0.0;
   const bool mine = (cta % world) == rank;
+  const unsigned long long nmax_bits = __ldg(norm_max_bits);
   if (mine && !(symmetric && ct0 + MMD_STRIP - 1 < rt)) {
+    const bool expand = nmax_bits <= (unsigned long long)__double_as_longlong(MMD_EXPAND_LIMIT);
     const long long i = (long long)rt * MMD_TILE + threadIdx.x;
     double pi[DP];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) pi[k] = Ps[(size_t)k * np_pad + i];
+    for (int k = 0; k < DP; ++k) pi[k] = Ps[(size_t)k * np_pad + i] * (expand ? -2.0 : 1.0);
+    const double pn = Ps[(size_t)DP * np_pad + i];
     const bool row_ok = i < np;
     for (int ct = ct0; ct < min(ct0 + MMD_STRIP, n_ct); ++ct) {
       if (symmetric && ct < rt) continue;
       __syncthreads();
 #pragma unroll
-      for (int k = 0; k < DP; ++k) sq[k][threadIdx.x] = Qs[(size_t)k * nq_pad + (size_t)ct * MMD_TILE + threadIdx.x];
+      for (int k = 0; k <= DP; ++k) sq[k][threadIdx.x] = Qs[(size_t)k * nq_pad + (size_t)ct * MMD_TILE + threadIdx.x];
       __syncthreads();
       const int jmax = (int)min((long long)MMD_TILE, nq - (long long)ct * MMD_TILE);
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      int jj = 0;
-      for (; jj + 4 <= jmax; jj += 4) {
-        double r2[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int k = 0; k < DP; ++k) {
-          const double2 q01 = *reinterpret_cast<const double2*>(&sq[k][jj]);
-          const double2 q23 = *reinterpret_cast<const double2*>(&sq[k][jj + 2]);
-          double t0 = pi[k] - q01.x, t1 = pi[k] - q01.y, t2 = pi[k] - q23.x, t3 = pi[k] - q23.y;
-          r2[0] = fma(t0, t0, r2[0]); r2[1] = fma(t1, t1, r2[1]); r2[2] = fma(t2, t2, r2[2]); r2[3] = fma(t3, t3, r2[3]);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] += kernel_from_r2<KERNEL>(r2[e]);
-      }
-      for (; jj < jmax; ++jj) {
-        double r2 = 0.0;
-#pragma unroll
-        for (int k = 0; k < DP; ++k) { const double t = pi[k] - sq[k][jj]; r2 = fma(t, t, r2); }
-        acc[0] += kernel_from_r2<KERNEL>(r2);
-      }
+      const double s = expand ? mmd_tile_sum<KERNEL, DP, true>(pi, pn, sq, jmax, exp_tab)
+                              : mmd_tile_sum<KERNEL, DP, false>(pi, pn, sq, jmax, exp_tab);
       const double w = (symmetric && ct != rt) ? 2.0 : 1.0;
-      if (row_ok) total += w * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+      if (row_ok) total += w * s;
     }
   }
   red[threadIdx.x] = total;
@@ -72,7 +111,7 @@ mmd_kernel(const double* __restrict__ Ps, long long np, long long np_pad, const 
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[cta] = red[0];
+  if (threadIdx.x == 0) partial[cta] = nmax_bits > 0x7ff0000000000000ull ? NAN : red[0];
 }
 
 // fixed-order tree sum of `n` partials into out[0] (one block)
@@ -89,26 +128,60 @@ __global__ void __launch_bounds__(1024) tree_sum_kernel(const double* __restrict
   if (threadIdx.x == 0) out[0] = red[0];
 }
 
-// AoS d x n (column-major) -> scaled SoA [dp][n_pad]
-__global__ void mmd_scale_kernel(const double* __restrict__ P, long long n, long long n_pad, int d, int dp,
-                                 const double* __restrict__ scale, double* __restrict__ Ps) {
+// centre[k] = mean of coordinate k over the first min(n, 4096) points of P (one block; any fixed point near the data would do:
+// the kernels are stationary, the centre only keeps the norms small)
+__global__ void __launch_bounds__(256) mmd_centre_kernel(const double* __restrict__ P, long long n, int d, double* __restrict__ centre) {
+  __shared__ double red[256];
+  const int cnt = (int)min(n, 4096LL);
+  for (int k = 0; k < d; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += 256) s += P[(size_t)k + (size_t)d * i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { const double c = red[0] / cnt; centre[k] = isfinite(c) ? c : 0.0; }
+    __syncthreads();
+  }
+}
+
+// AoS d x n (column-major) -> centred, scaled SoA [dp + 1][n_pad] with the squared norm in row dp; records the largest norm
+__global__ void __launch_bounds__(256)
+mmd_scale_kernel(const double* __restrict__ P, long long n, long long n_pad, int d, int dp, const double* __restrict__ scale,
+                 const double* __restrict__ centre, double* __restrict__ Ps, unsigned long long* __restrict__ norm_max_bits) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y;
-  if (i >= n_pad) return;
-  Ps[(size_t)k * n_pad + i] = (i < n && k < d) ? P[(size_t)k + (size_t)d * i] * scale[k] : 0.0;
+  double nrm = 0.0;
+  if (i < n_pad) {
+    for (int k = 0; k < dp; ++k) {
+      const double v = (i < n && k < d) ? (P[(size_t)k + (size_t)d * i] - centre[k]) * scale[k] : 0.0;
+      Ps[(size_t)k * n_pad + i] = v;
+      nrm = fma(v, v, nrm);
+    }
+    Ps[(size_t)dp * n_pad + i] = nrm;
+  }
+  // positive doubles order like their bit patterns; +Inf marks "too wide for the expanded form", a NaN pattern (above +Inf)
+  // marks NaN coordinates, which poison the result as they do in the reference
+  unsigned long long b = (unsigned long long)__double_as_longlong(nrm);
+  if (!(nrm <= MMD_EXPAND_LIMIT) && nrm == nrm) b = 0x7ff0000000000000ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, b, o); b = y > b ? y : b; }
+  if ((threadIdx.x & 31) == 0 && b) atomicMax(norm_max_bits, b);
 }
 
 template <int KERNEL, int DP>
 static void mmd_launch(const double* Ps, long long np, long long npp, const double* Qs, long long nq, long long nqp, int sym,
-                       int rank, int world, double* partial, dim3 grid, cudaStream_t st) {
-  mmd_kernel<KERNEL, DP><<<grid, MMD_TILE, 0, st>>>(Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial);
+                       int rank, int world, const unsigned long long* nmax, double* partial, dim3 grid, cudaStream_t st) {
+  mmd_kernel<KERNEL, DP><<<grid, MMD_TILE, 0, st>>>(Ps, np, npp, Qs, nq, nqp, sym, rank, world, nmax, partial);
 }
 
 template <int KERNEL>
 static int mmd_launch_k(Ctx* ctx, int dp, const double* Ps, long long np, long long npp, const double* Qs, long long nq,
-                        long long nqp, int sym, int rank, int world, double* partial, dim3 grid, cudaStream_t st) {
+                        long long nqp, int sym, int rank, int world, const unsigned long long* nmax, double* partial, dim3 grid,
+                        cudaStream_t st) {
 #define BOSIP_DP_CASE(DPV) \
-  case DPV: mmd_launch<KERNEL, DPV>(Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st); break;
+  case DPV: mmd_launch<KERNEL, DPV>(Ps, np, npp, Qs, nq, nqp, sym, rank, world, nmax, partial, grid, st); break;
   switch (dp) {
     BOSIP_DP_CASE(2) BOSIP_DP_CASE(3) BOSIP_DP_CASE(4) BOSIP_DP_CASE(5) BOSIP_DP_CASE(6) BOSIP_DP_CASE(8)
     BOSIP_DP_CASE(10) BOSIP_DP_CASE(12) BOSIP_DP_CASE(16) BOSIP_DP_CASE(24) BOSIP_DP_CASE(32)
@@ -120,14 +193,14 @@ static int mmd_launch_k(Ctx* ctx, int dp, const double* Ps, long long np, long l
 }
 
 static int mmd_pair(Ctx* ctx, int kernel_id, int dp, const double* Ps, long long np, long long npp, const double* Qs,
-                    long long nq, long long nqp, int sym, int rank, int world, double* partial, double* out,
-                    cudaStream_t st) {
+                    long long nq, long long nqp, int sym, int rank, int world, const unsigned long long* nmax, double* partial,
+                    double* out, cudaStream_t st) {
   dim3 grid((unsigned)(npp / MMD_TILE), (unsigned)((nqp / MMD_TILE + MMD_STRIP - 1) / MMD_STRIP));
   const long long nparts = (long long)grid.x * grid.y;
   switch (kernel_id) {
-    case 0: BOSIP_TRY((mmd_launch_k<0>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st))); break;
-    case 1: BOSIP_TRY((mmd_launch_k<1>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st))); break;
-    case 2: BOSIP_TRY((mmd_launch_k<2>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, partial, grid, st))); break;
+    case 0: BOSIP_TRY((mmd_launch_k<0>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, nmax, partial, grid, st))); break;
+    case 1: BOSIP_TRY((mmd_launch_k<1>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, nmax, partial, grid, st))); break;
+    case 2: BOSIP_TRY((mmd_launch_k<2>(ctx, dp, Ps, np, npp, Qs, nq, nqp, sym, rank, world, nmax, partial, grid, st))); break;
     default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown kernel id");
   }
   tree_sum_kernel<<<1, 1024, 0, st>>>(partial, nparts, out);
@@ -152,8 +225,8 @@ int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double*
   const long long max_parts = max_tiles * ((max_tiles + MMD_STRIP - 1) / MMD_STRIP);
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  const size_t o_As = carve((size_t)dp * np * 8), o_Bs = carve((size_t)dp * mp * 8), o_scale = carve((size_t)dp * 8),
-               o_part = carve((size_t)max_parts * 8), o_out = carve(3 * 8);
+  const size_t o_As = carve((size_t)(dp + 1) * np * 8), o_Bs = carve((size_t)(dp + 1) * mp * 8), o_scale = carve((size_t)dp * 8),
+               o_centre = carve((size_t)dp * 8), o_nmax = carve(8), o_part = carve((size_t)max_parts * 8), o_out = carve(3 * 8);
   const size_t o_dA = mem == BOSIP_B200_HOST ? carve((size_t)d * n * 8) : 0, o_dB = mem == BOSIP_B200_HOST ? carve((size_t)d * m * 8) : 0;
   BOSIP_TRY(ensure_ws(ctx, off));
   auto D = [&](size_t o) { return reinterpret_cast<double*>(ctx->ws + o); };
@@ -165,12 +238,16 @@ int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double*
     BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_dB), B, (size_t)d * m * 8, cudaMemcpyHostToDevice, st));
     pA = D(o_dA); pB = D(o_dB);
   }
-  mmd_scale_kernel<<<dim3((unsigned)((np + 255) / 256), dp), 256, 0, st>>>(pA, n, np, d, dp, dscale, As);
-  mmd_scale_kernel<<<dim3((unsigned)((mp + 255) / 256), dp), 256, 0, st>>>(pB, m, mp, d, dp, dscale, Bs);
+  double* dcentre = D(o_centre);
+  unsigned long long* nmax = reinterpret_cast<unsigned long long*>(ctx->ws + o_nmax);
+  BOSIP_CUDA(ctx, cudaMemsetAsync(nmax, 0, 8, st));
+  mmd_centre_kernel<<<1, 256, 0, st>>>(pA, n, d, dcentre);
+  mmd_scale_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(pA, n, np, d, dp, dscale, dcentre, As, nmax);
+  mmd_scale_kernel<<<(unsigned)((mp + 255) / 256), 256, 0, st>>>(pB, m, mp, d, dp, dscale, dcentre, Bs, nmax);
   BOSIP_CUDA(ctx, cudaGetLastError());
-  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, As, n, np, As, n, np, 1, rank, world, partial, dout + 0, st));
-  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, Bs, m, mp, Bs, m, mp, 1, rank, world, partial, dout + 1, st));
-  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, As, n, np, Bs, m, mp, 0, rank, world, partial, dout + 2, st));
+  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, As, n, np, As, n, np, 1, rank, world, nmax, partial, dout + 0, st));
+  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, Bs, m, mp, Bs, m, mp, 1, rank, world, nmax, partial, dout + 1, st));
+  BOSIP_TRY(mmd_pair(ctx, kernel_id, dp, As, n, np, Bs, m, mp, 0, rank, world, nmax, partial, dout + 2, st));
   BOSIP_CUDA(ctx, cudaMemcpyAsync(sums, dout, 3 * 8, cudaMemcpyDeviceToHost, st));
   BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
   return 0;

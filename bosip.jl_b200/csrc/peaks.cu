@@ -66,14 +66,15 @@ int fp64_peak(Ctx* ctx, double* dmma, double* dfma) {
 // self-test of fastmath.cuh against the CUDA library (host buffers)
 __global__ void math_selftest_kernel(const double* __restrict__ x, long long n, int variant, double* __restrict__ e_fast,
                                      double* __restrict__ q_fast, double* __restrict__ e_ref, double* __restrict__ q_ref) {
-  __shared__ double tab[64];
-  load_exp_table(tab);
+  __shared__ double tab_all[64 * 8];
+  load_exp_table<8>(tab_all);
+  const double* tab = exp_table_lane<8>(tab_all);
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double v = x[i];
   if (variant == 0) { e_fast[i] = fast_exp_neg(v); q_fast[i] = fast_sqrt(v); }
-  else { e_fast[i] = fast_exp_neg_t(v, tab); q_fast[i] = fast_sqrt1(v); }
+  else { e_fast[i] = fast_exp_neg_t<8>(v, tab); q_fast[i] = fast_sqrt1(v); }
   e_ref[i] = exp(-v); q_ref[i] = sqrt(v);
 }
 

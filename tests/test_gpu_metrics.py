@@ -52,6 +52,26 @@ def test_mmd_properties(bb, ctx):
     assert bb.calculate_metric(bb.MMDMetric(k), A, B, ctx) == bb.calc_mmd(k, A, B, ctx)
 
 
+@pytest.mark.parametrize("kernel_id", [0, 1, 2])
+def test_mmd_distance_forms(bb, ctx, kernel_id):
+    """The pair kernel forms squared distances as |p|^2 + |q|^2 - 2 p.q when all centred norms are small and as
+    sum (p - q)^2 otherwise (csrc/metrics.cu); both agree with the oracle, and a common translation changes nothing."""
+    rng = np.random.default_rng(17 + kernel_id)
+    d, n, m = 4, 1500, 1100
+    lam = rng.uniform(0.8, 1.5, d); k = bb.Kernel(kernel_id, lam)
+    A = 0.4 * rng.standard_normal((d, n)); B = 0.1 + 0.5 * rng.standard_normal((d, m))          # compact: expanded form
+    v = bb.calc_mmd(k, A, B, ctx)
+    assert v == pytest.approx(orc.calc_mmd(kernel_id, lam, A, B)[0], rel=1e-10, abs=1e-14)
+    shift = np.array([1e3, -2e3, 5e2, 7e3])[:, None]                                               # centring removes the offset
+    assert bb.calc_mmd(k, A + shift, B + shift, ctx) == pytest.approx(v, rel=1e-8, abs=1e-13)
+    Aw = 30.0 * rng.standard_normal((d, n)); Bw = 3.0 + 33.0 * rng.standard_normal((d, m))         # many length-scales wide: difference form
+    assert bb.calc_mmd(k, Aw, Bw, ctx) == pytest.approx(orc.calc_mmd(kernel_id, lam, Aw, Bw)[0], rel=1e-10, abs=1e-14)
+    Bfar = B + 1e4                                                                                 # the two sets far apart: cross term underflows to 0
+    assert bb.calc_mmd(k, A, Bfar, ctx) == pytest.approx(orc.calc_mmd(kernel_id, lam, A, Bfar)[0], rel=1e-10)
+    An = A.copy(); An[1, 7] = np.nan
+    assert np.isnan(bb.calc_mmd(k, An, B, ctx))
+
+
 def test_tv_goldens_and_oracle(bb, ctx):
     for c in GOLD["tv"]:
         assert bb.calc_tv(c["log_ws"], c["a"], c["t"], ctx) == pytest.approx(c["tv"], rel=1e-10, abs=1e-16)
