@@ -812,6 +812,10 @@ def calc_tv(log_ws, approx_logvals, true_logvals, ctx: Optional[Context] = None)
     kw, pw, mem, G = _colmajor(log_ws); ka, pa, m2, _ = _colmajor(approx_logvals); kt, pt, m3, _ = _colmajor(true_logvals)
     if not (mem == m2 == m3):
         raise ValueError("inputs must live in the same memory space")
+    if parallel.rank_world()[1] == 1:      # one GPU: both stages in one call, host vectors uploaded once
+        out = np.zeros(1)
+        ctx._check(ctx.lib.bosip_b200_tv(ctx.h, pw, pa, pt, G, mem, _dptr(out)))
+        return float(out[0])
     s1 = np.zeros(4)
     ctx._check(ctx.lib.bosip_b200_tv_stage1(ctx.h, pw, pa, pt, G, mem, _dptr(s1)))
     (ma, sa), (mt, st_), Gtot = parallel.lse_allgather(s1[0], s1[1]), parallel.lse_allgather(s1[2], s1[3]), parallel.allreduce_count(G)

@@ -810,16 +810,7 @@ int bosip_b200_tv_stage2(bosip_b200_ctx* h, const double* lw, const double* a, c
 int bosip_b200_tv(bosip_b200_ctx* h, const double* lw, const double* a, const double* t, int64_t G, int mem, double* tv_out) {
   API_LOCK(h);
   if (!tv_out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
-  double s1[4], s2[2];
-  BOSIP_TRY(tv_stage1(ctx, lw, a, t, G, mem, s1));
-  // logmeanexp = logsumexp - log(G); logsumexp returns the max itself when it is infinite (src/utils/utils.jl:9)
-  const double lg = log((double)G);
-  const double eva = isinf(s1[0]) ? s1[0] : s1[0] + log(s1[1]) - lg;
-  const double evt = isinf(s1[2]) ? s1[2] : s1[2] + log(s1[3]) - lg;
-  BOSIP_TRY(tv_stage2(ctx, lw, a, t, G, mem, eva, evt, s2));
-  const double lme = isinf(s2[0]) ? s2[0] : s2[0] + log(s2[1]) - lg;
-  *tv_out = 0.5 * exp(lme);
-  return 0;
+  return tv_full(ctx, lw, a, t, G, mem, tv_out);
 }
 
 int bosip_b200_mvnormal_sample(bosip_b200_ctx* h, int d, const double* mu, const double* L, uint64_t seed, int64_t offset, int64_t M,

@@ -200,6 +200,7 @@ int mmd_sums(Ctx* ctx, int kernel_id, int d, const double* lambda, const double*
 int tv_stage1(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* out4);
 int tv_stage2(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double eva,
               double evt, double* out2);
+int tv_full(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* tv_out);
 // sampler.cu
 int mvn_sample(Ctx* ctx, int d, const double* mu, const double* L, uint64_t seed, int64_t offset, int64_t m, int mem, double* out);
 int mix_pdf_sum(Ctx* ctx, int d, int nq, const double* mus, const double* Linvs, const double* lognorm, const double* X, int64_t m, int mem,

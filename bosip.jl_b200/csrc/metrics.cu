@@ -267,16 +267,16 @@ __host__ __device__ inline Lse lse_merge(Lse a, Lse b) {
 // Scaled-sum accumulator: value = exp(m) * s.  Batches of TV_B elements are folded with ONE rescale and TV_B independent
 // branch-free exps (fastmath.cuh), instead of a serial, branchy online update per element.
 constexpr int TV_B = 4;
-__device__ __forceinline__ void lse_push_batch(Lse& acc, const double (&v)[TV_B]) {
+__device__ __forceinline__ void lse_push_batch(Lse& acc, const double (&v)[TV_B], const double* exp_tab) {
   double vm = v[0];
 #pragma unroll
   for (int e = 1; e < TV_B; ++e) vm = fmax(vm, v[e]);
   if (vm == -INFINITY) return;                        // nothing to add
   if (vm == INFINITY) { acc.m = INFINITY; acc.s = 1.0; return; }
   const double nm = fmax(acc.m, vm);
-  double s = (acc.m == -INFINITY) ? 0.0 : acc.s * fast_exp_neg(nm - acc.m);
+  double s = (acc.m == -INFINITY) ? 0.0 : acc.s * fast_exp_neg_t<1>(nm - acc.m, exp_tab);
 #pragma unroll
-  for (int e = 0; e < TV_B; ++e) s += fast_exp_neg(nm - v[e]);   // v = -Inf -> exp(-Inf) = 0
+  for (int e = 0; e < TV_B; ++e) s += fast_exp_neg_t<1>(nm - v[e], exp_tab);   // v = -Inf -> exp(-Inf) = 0
   acc.m = nm; acc.s = s;
 }
 __device__ __forceinline__ Lse lse_block(Lse x, Lse* sh) {
@@ -307,6 +307,9 @@ __global__ void __launch_bounds__(256)
 tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
                  double* __restrict__ out) {
   __shared__ Lse sh[8];
+  __shared__ double exp_tab[64];
+  load_exp_table<1>(exp_tab);
+  __syncthreads();
   Lse la{-INFINITY, 0.0}, lt{-INFINITY, 0.0};
   const long long per = (G + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
@@ -320,8 +323,8 @@ tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, co
       va[e] = ok ? w + a[i] : -INFINITY;
       vt[e] = ok ? w + t[i] : -INFINITY;
     }
-    lse_push_batch(la, va);
-    lse_push_batch(lt, vt);
+    lse_push_batch(la, va, exp_tab);
+    lse_push_batch(lt, vt, exp_tab);
   }
   la = lse_block(la, sh);
   lt = lse_block(lt, sh);
@@ -332,8 +335,14 @@ tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, co
 // reference's `log.(diffs)` is never taken: each term is formed directly at the running scale m >= lw + max(a~, t~).
 __global__ void __launch_bounds__(256)
 tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
-                 double eva, double evt, int a_inf, int t_inf, double* __restrict__ out) {
+                 double eva_v, double evt_v, const double* __restrict__ ev_dev, double* __restrict__ out) {
   __shared__ Lse sh[8];
+  __shared__ double exp_tab[64];
+  load_exp_table<1>(exp_tab);
+  __syncthreads();
+  // the normalisers come by value (staged calls, combined across ranks on the host) or from the merge kernel of stage 1
+  const double eva = ev_dev ? ev_dev[0] : eva_v, evt = ev_dev ? ev_dev[1] : evt_v;
+  const bool a_inf = isinf(eva), t_inf = isinf(evt);   // all-(-Inf) vector: its normalised density is all -Inf (tv.jl:64-66)
   Lse ld{-INFINITY, 0.0};
   const long long per = (G + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
@@ -352,37 +361,27 @@ tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, co
     if (vm == -INFINITY) continue;
     if (vm == INFINITY) { ld.m = INFINITY; ld.s = 1.0; continue; }
     const double nm = fmax(ld.m, vm);
-    double s = (ld.m == -INFINITY) ? 0.0 : ld.s * fast_exp_neg(nm - ld.m);
+    double s = (ld.m == -INFINITY) ? 0.0 : ld.s * fast_exp_neg_t<1>(nm - ld.m, exp_tab);
 #pragma unroll
-    for (int e = 0; e < TV_B; ++e) s += fabs(fast_exp_neg(nm - ua[e]) - fast_exp_neg(nm - ut[e]));
+    for (int e = 0; e < TV_B; ++e) s += fabs(fast_exp_neg_t<1>(nm - ua[e], exp_tab) - fast_exp_neg_t<1>(nm - ut[e], exp_tab));
     ld.m = nm; ld.s = s;
   }
   ld = lse_block(ld, sh);
   if (threadIdx.x == 0) { out[2 * blockIdx.x + 0] = ld.m; out[2 * blockIdx.x + 1] = ld.s; }
 }
 
-static int tv_common(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, int stage, double eva,
-                     double evt, double* out) {
-  if (G < 1 || !lw || !a || !t || !out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad TV arguments");
+static int tv_blocks(Ctx* ctx, int64_t G) {
+  return (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 8 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 8);
+}
+static size_t tv_part_bytes(int nblocks) { return ((size_t)nblocks * 4 * 8 + 3 * 8 + 255) / 256 * 256; }
+
+// one stage on device-resident vectors; dpart: nblocks * 4 doubles of scratch; out: the merged (max, sum) pairs
+static int tv_run(Ctx* ctx, const double* pl, const double* pa, const double* pt, int64_t G, int stage, double eva, double evt,
+                  double* dpart, int nblocks, double* out) {
   cudaStream_t st = ctx->s_comp;
-  const int nblocks = (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 8 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 8);
   const int width = stage == 1 ? 4 : 2;
-  const size_t part_bytes = ((size_t)nblocks * width * 8 + 255) / 256 * 256;
-  const size_t vec_bytes = ((size_t)G * 8 + 255) / 256 * 256;
-  BOSIP_TRY(ensure_ws(ctx, part_bytes + (mem == BOSIP_B200_HOST ? 3 * vec_bytes : 0)));
-  double* dpart = reinterpret_cast<double*>(ctx->ws);
-  const double *pl = lw, *pa = a, *pt = t;
-  if (mem == BOSIP_B200_HOST) {
-    double* dl = reinterpret_cast<double*>(ctx->ws + part_bytes);
-    double* da = reinterpret_cast<double*>(ctx->ws + part_bytes + vec_bytes);
-    double* dt = reinterpret_cast<double*>(ctx->ws + part_bytes + 2 * vec_bytes);
-    BOSIP_CUDA(ctx, cudaMemcpyAsync(dl, lw, (size_t)G * 8, cudaMemcpyHostToDevice, st));
-    BOSIP_CUDA(ctx, cudaMemcpyAsync(da, a, (size_t)G * 8, cudaMemcpyHostToDevice, st));
-    BOSIP_CUDA(ctx, cudaMemcpyAsync(dt, t, (size_t)G * 8, cudaMemcpyHostToDevice, st));
-    pl = dl; pa = da; pt = dt;
-  }
   if (stage == 1) tv_stage1_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, dpart);
-  else tv_stage2_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, eva, evt, isinf(eva) ? 1 : 0, isinf(evt) ? 1 : 0, dpart);
+  else tv_stage2_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, eva, evt, nullptr, dpart);
   BOSIP_CUDA(ctx, cudaGetLastError());
   std::vector<double> h((size_t)nblocks * width);
   BOSIP_CUDA(ctx, cudaMemcpyAsync(h.data(), dpart, h.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -395,11 +394,75 @@ static int tv_common(Ctx* ctx, const double* lw, const double* a, const double* 
   return 0;
 }
 
+// workspace = [partials][lw][a][t]; host vectors are uploaded ONCE (both stages of tv_full read the same device copies)
+static int tv_stage_inputs(Ctx* ctx, const double*& lw, const double*& a, const double*& t, int64_t G, int mem, int nblocks, double** dpart) {
+  if (G < 1 || !lw || !a || !t) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad TV arguments");
+  const size_t part_bytes = tv_part_bytes(nblocks);
+  const size_t vec_bytes = ((size_t)G * 8 + 255) / 256 * 256;
+  BOSIP_TRY(ensure_ws(ctx, part_bytes + (mem == BOSIP_B200_HOST ? 3 * vec_bytes : 0)));
+  *dpart = reinterpret_cast<double*>(ctx->ws);
+  if (mem == BOSIP_B200_HOST) {
+    cudaStream_t st = ctx->s_comp;
+    double* dl = reinterpret_cast<double*>(ctx->ws + part_bytes);
+    double* da = reinterpret_cast<double*>(ctx->ws + part_bytes + vec_bytes);
+    double* dt = reinterpret_cast<double*>(ctx->ws + part_bytes + 2 * vec_bytes);
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(dl, lw, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(da, a, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    BOSIP_CUDA(ctx, cudaMemcpyAsync(dt, t, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    lw = dl; a = da; t = dt;
+  }
+  return 0;
+}
+
 int tv_stage1(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* out4) {
-  return tv_common(ctx, lw, a, t, G, mem, 1, 0.0, 0.0, out4);
+  if (!out4) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad TV arguments");
+  const int nblocks = tv_blocks(ctx, G);
+  double* dpart = nullptr;
+  BOSIP_TRY(tv_stage_inputs(ctx, lw, a, t, G, mem, nblocks, &dpart));
+  return tv_run(ctx, lw, a, t, G, 1, 0.0, 0.0, dpart, nblocks, out4);
 }
 int tv_stage2(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double eva, double evt, double* out2) {
-  return tv_common(ctx, lw, a, t, G, mem, 2, eva, evt, out2);
+  if (!out2) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "bad TV arguments");
+  const int nblocks = tv_blocks(ctx, G);
+  double* dpart = nullptr;
+  BOSIP_TRY(tv_stage_inputs(ctx, lw, a, t, G, mem, nblocks, &dpart));
+  return tv_run(ctx, lw, a, t, G, 2, eva, evt, dpart, nblocks, out2);
+}
+
+// Device-side merge of the per-block (max, sum) pairs in a fixed order (strided partial merges, then the block tree).
+// stage 1: ev[0..1] = logmeanexp of lw + a and of lw + t;  stage 2: ev[2] = TV = exp(logmeanexp(...)) / 2.
+// logmeanexp = logsumexp - log(G); logsumexp returns the max itself when it is infinite (src/utils/utils.jl:9)
+__global__ void __launch_bounds__(256) tv_merge_kernel(const double* __restrict__ part, int nblocks, int stage, double log_g, double* __restrict__ ev) {
+  __shared__ Lse sh[8];
+  const int width = stage == 1 ? 4 : 2;
+  for (int c = 0; c < width / 2; ++c) {
+    Lse acc{-INFINITY, 0.0};
+    for (int b = threadIdx.x; b < nblocks; b += 256) acc = lse_merge(acc, Lse{part[(size_t)b * width + 2 * c], part[(size_t)b * width + 2 * c + 1]});
+    acc = lse_block(acc, sh);
+    if (threadIdx.x == 0) {
+      const double lme = isinf(acc.m) ? acc.m : acc.m + log(acc.s) - log_g;
+      if (stage == 1) ev[c] = lme; else ev[2] = 0.5 * exp(lme);
+    }
+    __syncthreads();
+  }
+}
+
+// calc_tv on one GPU (tv.jl:59-73): inputs uploaded once, both stages and their merges queued back to back, one 8-byte read-back
+int tv_full(Ctx* ctx, const double* lw, const double* a, const double* t, int64_t G, int mem, double* tv_out) {
+  const int nblocks = tv_blocks(ctx, G);
+  double* dpart = nullptr;
+  BOSIP_TRY(tv_stage_inputs(ctx, lw, a, t, G, mem, nblocks, &dpart));
+  cudaStream_t st = ctx->s_comp;
+  double* ev = dpart + (size_t)nblocks * 4;   // 3 doubles behind the partials (tv_part_bytes reserves them)
+  const double lg = log((double)G);
+  tv_stage1_kernel<<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, dpart);
+  tv_merge_kernel<<<1, 256, 0, st>>>(dpart, nblocks, 1, lg, ev);
+  tv_stage2_kernel<<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, 0.0, 0.0, ev, dpart);
+  tv_merge_kernel<<<1, 256, 0, st>>>(dpart, nblocks, 2, lg, ev);
+  BOSIP_CUDA(ctx, cudaGetLastError());
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(tv_out, ev + 2, 8, cudaMemcpyDeviceToHost, st));
+  BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  return 0;
 }
 
 }  // namespace bosip
