@@ -280,7 +280,8 @@ int bosip_b200_mmd(bosip_b200_ctx* ctx, int kernel_id, int d, const double* lamb
 /* stage 1: out[4] = {max(lw+a), sum exp(lw+a-max), max(lw+t), sum exp(lw+t-max)} over this rank's G points.
  * stage 2: given the global ev_approx/ev_true (logmeanexp), out[2] = {m, s} with
  *          exp(m) * s = sum_i exp(lw_i) |exp(a_i-ev_a) - exp(t_i-ev_t)|  (a scaled sum: pairs from several ranks merge like
- *          log-sum-exp pairs; TV = 0.5 * exp(m + log s - log G)).   bosip_b200_tv = both stages on one GPU. */
+ *          log-sum-exp pairs; TV = 0.5 * exp(m + log s - log G)).   bosip_b200_tv = both stages on one GPU: host vectors
+ *          are uploaded once, the stages and their merges run back to back on the device, 8 bytes come back. */
 int bosip_b200_tv_stage1(bosip_b200_ctx* ctx, const double* log_ws, const double* a, const double* t, int64_t G,
                          int mem, double* out4);
 int bosip_b200_tv_stage2(bosip_b200_ctx* ctx, const double* log_ws, const double* a, const double* t, int64_t G,

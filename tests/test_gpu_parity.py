@@ -375,3 +375,31 @@ def test_marginal_integration_sweep(bb, ctx, func, key):
     step = (pr.ub - pr.lb) / (gs - 1)
     ys = rn["marginals"][(0, 0)]["ys"]
     assert (ys.sum() - 0.5 * (ys[0] + ys[-1])) * step[0] == pytest.approx(1.0, rel=1e-12)
+
+
+def test_concurrent_calls_on_one_context(bb, ctx):
+    """SURVEY.md section 8b, threading: BOSS may call the closures from several threads (parallel multistart, threaded candidate
+    evaluation).  Calls on one context serialise on its mutex; results are bit-identical to the serial ones."""
+    import threading
+    pr, model, like, prior, *_ = problem(bb, "C2")
+    post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
+    sets = [queries(pr, 3000 + 517 * i, seed=40 + i) for i in range(6)]
+    serial = [bb.posterior_eval(post, like, prior, Xq, 7, acq=bb.MaxVar()) for Xq in sets]
+    out, errs = [None] * len(sets), []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                out[i] = bb.posterior_eval(post, like, prior, sets[i], 7, acq=bb.MaxVar())
+                k = bb.Kernel(bb.SE, np.ones(pr.d))
+                bb.calc_mmd(k, sets[i][:, :400], sets[i][:, 400:900], ctx)          # a different entry point in between
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(sets))]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    for r, s in zip(out, serial):
+        for key in ("log_approx_post", "log_post_mean", "log_post_var"):
+            assert np.array_equal(r[key], s[key], equal_nan=True)
+        assert r["best_idx"] == s["best_idx"] and r["best_val"] == s["best_val"]
