@@ -289,7 +289,9 @@ def main():
             "whole_path_tflops_as_written": sum(fl.values()) * value / world * 1e-12,
             "argmax": {"global_index": int(winner[0]), "value": float(winner[1])},
         }
-        if not args.no_cpu_baseline:
+        if world > 1:
+            out["cpu_baseline"] = None      # timed at N=1 only (the other ranks would sit in the barrier for 20-30 s of CPU work)
+        elif not args.no_cpu_baseline:
             Xs = bb.synth.philox_uniform_candidates(SEED, 0, CPU_SAMPLE, pr.lb, pr.ub)
             cpu_reference_pass(pr, Xs[:, :8192])
             t0 = time.perf_counter()
