@@ -8,14 +8,15 @@
 // with a + b = g share the weight 2^-8g and accumulate in ONE TMEM accumulator.  Pairs with a + b >= S are below the kept
 // precision (2^-8S relative to the row scale) and are skipped, which leaves S(S+1)/2 INT8 GEMMs.  The FP64 value
 //     v[i,n] = 2^(f_n-13) * sum_g 2^-8g D_g[i,n]
-// is assembled in the epilogue (Horner, exact int->double conversions), squared and added to the row sum.
+// is assembled in the epilogue (one int64 per column for S <= 7, an FP64 Horner chain for S = 8), squared and added to the row sum.
 //
 // Shape of one CTA step: query tile 128 rows (MMA M) x 64 rows of L^{-1} (n-tile) x one 128-byte k-block.  All S group
 // accumulators of the n-tile are live at once (S x 64 TMEM columns <= 512), so every operand tile is loaded exactly once per
 // (n-tile, k-block).  For slice a of the query tile the B operands it meets are the slices b = 0..S-1-a; they are stored
 // contiguously in descending b, so up to four of them form ONE tcgen05.mma of N = 256 whose output columns are four
-// adjacent group accumulators.  Roles: warp 0 = TMA producer (cp.async.bulk, full/empty mbarriers), warp 1 = TMEM allocation
-// + the single MMA-issuing thread, warps 2..9 = epilogue (tcgen05.ld, FP64 assembly, row sums).
+// adjacent group accumulators.  Roles: warp 0 = TMA producer (cp.async.bulk, full/empty mbarriers), warp 1 = TMEM allocation,
+// warps 1 and 10 = one MMA-issuing thread each on disjoint slice rows, warps 2..9 = epilogue (tcgen05.ld, int64 assembly of the
+// groups, FP64 row sums).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -129,13 +130,9 @@ __device__ __forceinline__ double i32_to_f64(uint32_t v) {  // exact: 2^52 + 2^3
 __device__ unsigned long long i8_dbg[32];
 __device__ long long i8_ts[16][512];
 __device__ long long i8_tw[2][8][512];   // per epilogue warp: [0] past the t_full wait, [1] first group released   // per-tile timestamps of block 0 (plain stores: cheap)
-#define I8_T0() do {} while (0)
-#define I8_ACC(slot) do {} while (0)
 #define I8_TS(ev, tile) do { if (blockIdx.x == 0 && (tile) < 512) i8_ts[ev][tile] = clock64(); } while (0)
 #define I8_TW(ev, w, tile) do { if (blockIdx.x == 0 && (tile) < 512) i8_tw[ev][w][tile] = clock64(); } while (0)
 #else
-#define I8_T0() do {} while (0)
-#define I8_ACC(slot) do {} while (0)
 #define I8_TS(ev, tile) do {} while (0)
 #define I8_TW(ev, w, tile) do {} while (0)
 #endif
@@ -168,7 +165,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
       const int k_end = min(g.N, I8_BN * (t + 1));
       for (int kb = 0; kb < nkb; ++kb) {
         const uint32_t bs = b_cnt & 1;
-        { I8_T0(); mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1, 10 + Q); I8_ACC(Q * 4 + 0); }
+        mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1, 10 + Q);
         const uint32_t b_lo = b_lo0 + bs * (uint32_t)(Cfg::B_SET >> 4);
         const int nks = min(4, (k_end - kb * I8_BK + 31) >> 5);
         int waited = S;  // groups >= waited have been claimed by this thread for this tile
@@ -178,16 +175,14 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
           // slice a meets groups a .. S-1.  The epilogue hands every group back zeroed, so all MMAs accumulate and the next
           // tile starts on the low-order groups while the previous one is still draining the high-order ones.
           if (kb == 0) {
-            I8_T0();
 #pragma unroll
             for (int gi = S - 1; gi >= 0; --gi)
               if (gi >= a && gi < waited) mbar_wait_b(&t_empty[gi], tile_cnt & 1, 100 + 10 * Q + gi);
             if (waited == S) I8_TS(10 + Q, tile_cnt);   // first group wait of the tile satisfied
             waited = a;
-            I8_ACC(Q * 4 + 1);
           }
           const uint32_t as = (uint32_t)Cfg::ring_base(Q, NI) + a_cnt % Cfg::ring(Q, NI);   // this thread's own ring
-          { I8_T0(); mbar_wait_b(&a_full[as], (a_cnt / Cfg::ring(Q, NI)) & 1, 20 + Q); I8_ACC(Q * 4 + 2); }
+          mbar_wait_b(&a_full[as], (a_cnt / Cfg::ring(Q, NI)) & 1, 20 + Q);
           ++a_cnt;
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t a_lo = a_lo0 + as * (uint32_t)(I8_A_TILE >> 4);
@@ -204,7 +199,6 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
             }
           }
           umma_commit(&a_empty[as]);
-          I8_ACC(Q * 4 + 3);
         }
         umma_commit(&b_empty[bs]);
         ++b_cnt;
@@ -330,7 +324,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
         if (tid == 64) I8_TS(2, tile_cnt);       // accumulators complete
         if (lane == 0) I8_TW(0, ew, tile_cnt);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        I8_T0();
         // column scales of this thread's 32 columns: lane l fetches column l now (the load latency hides behind the Horner chain)
         // and the values are handed round by shuffles at the end -- 32 dependent global loads per thread took ~13 000 clk per tile
         const double my_cs = __ldg(csj + (size_t)t * I8_BN + 32 * half + lane);
