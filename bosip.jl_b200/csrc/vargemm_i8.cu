@@ -487,11 +487,13 @@ int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
     BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: N too large for exact integer accumulation (N < 8192)");
   if (gp->LinvI8) { cudaFree(gp->LinvI8); gp->LinvI8 = nullptr; }
   if (gp->cscale) { cudaFree(gp->cscale); gp->cscale = nullptr; }
+  gp->i8_S = 0;   // not prepared until everything below has succeeded
   const int N = gp->N, p = gp->p;
   const int T64 = (N + I8_BN - 1) / I8_BN, NP = T64 * I8_BN;
   const size_t sets = (size_t)i8_tile_off(T64);
   const size_t b_per_out = sets * S * I8_B_TILE;
   int* fexp = nullptr; double* dAlpha2 = nullptr;
+  struct Tmps { int** f; double** a; ~Tmps() { if (*f) cudaFree(*f); if (*a) cudaFree(*a); } } tmps{&fexp, &dAlpha2};  // freed on every exit path
   BOSIP_CUDA(ctx, cudaMalloc(&gp->LinvI8, b_per_out * p));
   BOSIP_CUDA(ctx, cudaMalloc(&gp->cscale, (size_t)p * NP * 8));
   BOSIP_CUDA(ctx, cudaMalloc(&fexp, (size_t)p * NP * 4));
@@ -507,7 +509,6 @@ int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
   }
   BOSIP_CUDA(ctx, cudaGetLastError());
   BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
-  cudaFree(fexp); cudaFree(dAlpha2);
   gp->i8_S = S; gp->i8_T64 = T64; gp->i8_b_per_out = b_per_out;
   return 0;
 }
