@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
   double* su = reinterpret_cast<double*>(smem_raw);          // [DP][nspan]
   double* sa = su + (size_t)DP * nspan;                       // [nspan]
   __shared__ __align__(8) uint64_t bar;
-  __shared__ double exp_tab_all[64 * KSTAR_EXP_REP];
+  __shared__ double exp_tab_all[EXP_TAB_N * KSTAR_EXP_REP];
   load_exp_table<KSTAR_EXP_REP>(exp_tab_all);
   const double* exp_tab = exp_table_lane<KSTAR_EXP_REP>(exp_tab_all);
 

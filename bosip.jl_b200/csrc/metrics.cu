@@ -74,7 +74,7 @@ mmd_kernel(const double* __restrict__ Ps, long long np, long long np_pad, const 
            double* __restrict__ partial) {
   __shared__ __align__(16) double sq[DP + 1][MMD_TILE];
   __shared__ double red[MMD_TILE];
-  __shared__ double exp_tab_all[64 * MMD_EXP_REP];
+  __shared__ double exp_tab_all[EXP_TAB_N * MMD_EXP_REP];
   load_exp_table<MMD_EXP_REP>(exp_tab_all);
   const double* exp_tab = exp_table_lane<MMD_EXP_REP>(exp_tab_all);
   const long long cta = (long long)blockIdx.y * gridDim.x + blockIdx.x;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256)
 tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
                  double* __restrict__ out) {
   __shared__ Lse sh[8];
-  __shared__ double exp_tab[64];
+  __shared__ double exp_tab[EXP_TAB_N];
   load_exp_table<1>(exp_tab);
   __syncthreads();
   Lse la{-INFINITY, 0.0}, lt{-INFINITY, 0.0};
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256)
 tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
                  double eva_v, double evt_v, const double* __restrict__ ev_dev, double* __restrict__ out) {
   __shared__ Lse sh[8];
-  __shared__ double exp_tab[64];
+  __shared__ double exp_tab[EXP_TAB_N];
   load_exp_table<1>(exp_tab);
   __syncthreads();
   // the normalisers come by value (staged calls, combined across ranks on the host) or from the merge kernel of stage 1

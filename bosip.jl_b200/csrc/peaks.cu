@@ -66,7 +66,7 @@ int fp64_peak(Ctx* ctx, double* dmma, double* dfma) {
 // self-test of fastmath.cuh against the CUDA library (host buffers)
 __global__ void math_selftest_kernel(const double* __restrict__ x, long long n, int variant, double* __restrict__ e_fast,
                                      double* __restrict__ q_fast, double* __restrict__ e_ref, double* __restrict__ q_ref) {
-  __shared__ double tab_all[64 * 8];
+  __shared__ double tab_all[EXP_TAB_N * 8];
   load_exp_table<8>(tab_all);
   const double* tab = exp_table_lane<8>(tab_all);
   __syncthreads();
