@@ -191,14 +191,38 @@ static int launch_k(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, i
   BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unsupported padded dimension");
 }
 
-int launch_kstar(Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan,
-                 void* Ks, double* mu_part, int write_k, int slices, cudaStream_t st) {
+// The 165 instantiations (3 kernels x 11 padded dimensions x 5 output modes) dominate the build time, so build.py compiles this file
+// once per kernel family (-DKSTAR_KERNEL_ID=0/1/2, in parallel); without the macro one translation unit holds all of them.
+#define KSTAR_ARGS_DECL Ctx* ctx, const Gp* gp, const double* xq, int64_t m_valid, int64_t mc, int64_t m_tiles, int nsplit, int nspan, \
+                        void* Ks, double* mu_part, int write_k, int slices, cudaStream_t st
+#define KSTAR_ARGS ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st
+#ifdef KSTAR_KERNEL_ID
+int launch_kstar_k0(KSTAR_ARGS_DECL);
+int launch_kstar_k1(KSTAR_ARGS_DECL);
+int launch_kstar_k2(KSTAR_ARGS_DECL);
+#if KSTAR_KERNEL_ID == 0
+int launch_kstar_k0(KSTAR_ARGS_DECL) { return launch_k<0>(KSTAR_ARGS); }
+#elif KSTAR_KERNEL_ID == 1
+int launch_kstar_k1(KSTAR_ARGS_DECL) { return launch_k<1>(KSTAR_ARGS); }
+#else
+int launch_kstar_k2(KSTAR_ARGS_DECL) { return launch_k<2>(KSTAR_ARGS); }
+#endif
+#else
+static int launch_kstar_k0(KSTAR_ARGS_DECL) { return launch_k<0>(KSTAR_ARGS); }
+static int launch_kstar_k1(KSTAR_ARGS_DECL) { return launch_k<1>(KSTAR_ARGS); }
+static int launch_kstar_k2(KSTAR_ARGS_DECL) { return launch_k<2>(KSTAR_ARGS); }
+#endif
+
+#if !defined(KSTAR_KERNEL_ID) || KSTAR_KERNEL_ID == 0
+int launch_kstar(KSTAR_ARGS_DECL) {
+  static_assert(BOSIP_B200_KERNEL_SE == 0 && BOSIP_B200_KERNEL_MATERN32 == 1 && BOSIP_B200_KERNEL_MATERN52 == 2, "kernel ids");
   switch (gp->kernel_id) {
-    case BOSIP_B200_KERNEL_SE: return launch_k<BOSIP_B200_KERNEL_SE>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
-    case BOSIP_B200_KERNEL_MATERN32: return launch_k<BOSIP_B200_KERNEL_MATERN32>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
-    case BOSIP_B200_KERNEL_MATERN52: return launch_k<BOSIP_B200_KERNEL_MATERN52>(ctx, gp, xq, m_valid, mc, m_tiles, nsplit, nspan, Ks, mu_part, write_k, slices, st);
+    case BOSIP_B200_KERNEL_SE: return launch_kstar_k0(KSTAR_ARGS);
+    case BOSIP_B200_KERNEL_MATERN32: return launch_kstar_k1(KSTAR_ARGS);
+    case BOSIP_B200_KERNEL_MATERN52: return launch_kstar_k2(KSTAR_ARGS);
   }
   BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown kernel id");
 }
+#endif
 
 }  // namespace bosip

@@ -10,7 +10,7 @@ base="${file%.cu}"
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c csrc/$file -o csrc/build/variants/${base}_$name.o
-  objs=$(ls csrc/build/*.o | grep -v "/$base.o")
+  objs=$(ls csrc/build/*.o | grep -v "/$base.o" | grep -v "/${base}_k[0-9].o")
   nvcc -shared -o csrc/build/variants/libbosip_b200_$name.so $objs csrc/build/variants/${base}_$name.o -gencode arch=compute_100a,code=sm_100a -lcudart
   echo built $name
 done
