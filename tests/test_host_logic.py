@@ -164,3 +164,28 @@ def test_gloo_world_size_2_exchange_steps(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in o, o
+
+
+def test_julia_glue_matches_header():
+    """The Julia side cannot run in this image, so at least every ccall in julia/BosipB200.jl and INTEGRATION.md names a symbol the
+    header declares and passes as many arguments as its prototype takes."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "bosip_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*)\s+(bosip_b200_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+        protos[m.group(1)] = [a for a in m.group(2).replace("\n", " ").split(",") if a.strip() and a.strip() != "void"]
+    seen = 0
+    for rel in (os.path.join("julia", "BosipB200.jl"), "INTEGRATION.md"):
+        src = open(os.path.join(root, rel)).read()
+        for m in re.finditer(r"ccall\(\(:(bosip_b200_\w+),\s*LIB\),\s*\w+,\s*\(", src):
+            name, i = m.group(1), m.end()
+            depth, k = 1, i
+            while depth:
+                depth += (src[k] == "(") - (src[k] == ")")
+                k += 1
+            types = [t for t in re.split(r",(?![^{]*\})", src[i:k - 1]) if t.strip()]
+            assert name in protos, f"{rel}: {name} is not declared in include/bosip_b200.h"
+            assert len(types) == len(protos[name]), f"{rel}: {name} passes {len(types)} arguments, the header takes {len(protos[name])}"
+            seen += 1
+    assert seen >= 25
