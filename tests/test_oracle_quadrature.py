@@ -72,3 +72,24 @@ def test_normal_sum_and_exp_expectations(seed):
     # ExpLikelihood: l(y) = exp(y), one output                                                                exp.jl:7-63
     m1, v1 = float(rng.normal(-1, 1)), float(rng.uniform(0.05, 1.5))
     check(orc.like_terms(orc.ExpLikelihood(), np.array([m1]), np.array([v1])), expect(np.exp, m1, v1), expect(lambda y: np.exp(2 * y), m1, v1))
+
+
+def test_prior_logpdfs_against_scipy():
+    """_log_prior (src/posterior/log_posterior.jl:228-229) over products of Uniform / Normal / truncated(Normal): the oracle's
+    closed forms against scipy.stats (an independent implementation of the same Distributions.jl semantics: -Inf outside the
+    support, boundaries included, truncation renormalised)."""
+    from scipy import stats
+    rng = np.random.default_rng(3)
+    kinds = [orc.UNIFORM, orc.NORMAL, orc.TRUNCNORMAL, orc.TRUNCNORMAL]
+    prm = [(-5.0, 5.0), (0.3, 1.7), (0.0, 5.0 / 3.0, -5.0, 5.0), (4.0, 0.5, -5.0, 5.0)]      # the last one is truncated well inside its bulk
+    prior = orc.ProductPrior(kinds, prm)
+    X = rng.uniform(-6, 6, (4, 400))
+    X[:, 0] = [-5.0, 0.0, 5.0, -5.0]                                                        # support boundaries are inside
+    ref = (stats.uniform(-5.0, 10.0).logpdf(X[0]) + stats.norm(0.3, 1.7).logpdf(X[1])
+           + stats.truncnorm((-5.0 - 0.0) / (5.0 / 3.0), (5.0 - 0.0) / (5.0 / 3.0), 0.0, 5.0 / 3.0).logpdf(X[2])
+           + stats.truncnorm((-5.0 - 4.0) / 0.5, (5.0 - 4.0) / 0.5, 4.0, 0.5).logpdf(X[3]))
+    got = orc.log_prior(prior, X)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin) and fin[0] and (~fin).sum() > 50
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-12, atol=1e-12)
+    assert orc.log_prior(prior, X[:, 0]) == pytest.approx(ref[0], rel=1e-12)                 # vector method
