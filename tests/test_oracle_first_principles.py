@@ -93,3 +93,23 @@ def test_prior_logpdfs_against_scipy():
     assert np.array_equal(np.isfinite(got), fin) and fin[0] and (~fin).sum() > 50
     np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-12, atol=1e-12)
     assert orc.log_prior(prior, X[:, 0]) == pytest.approx(ref[0], rel=1e-12)                 # vector method
+
+
+@pytest.mark.parametrize("kernel_id", [orc.SE, orc.MATERN32, orc.MATERN52])
+def test_gp_predict_against_sklearn(kernel_id):
+    """BOSS.mean / var (AbstractGPs posterior of alpha^2 k(./lambda) with noise sigma^2 on the training diagonal)
+    against scikit-learn's GaussianProcessRegressor with the hyper-parameters fixed -- an independent implementation of the same
+    textbook formulas and of the ARD SE / Matern-3/2 / Matern-5/2 kernels."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern
+    rng = np.random.default_rng(11 + kernel_id)
+    d, N, M = 3, 40, 25
+    X = rng.uniform(-5, 5, (d, N)); Y = (np.sin(X).sum(0) + 0.1 * rng.standard_normal(N))[None, :]
+    lam = rng.uniform(1.0, 4.0, (d, 1)); alpha = np.array([1.3]); sigma = np.array([0.2])
+    Xq = rng.uniform(-5, 5, (d, M)); Xq[:, :3] = X[:, :3] + 1e-3
+    mu, var = orc.gp_predict(orc.gp_fit(kernel_id, X, Y, lam, alpha, sigma), Xq)
+    base = RBF(length_scale=lam[:, 0]) if kernel_id == orc.SE else Matern(length_scale=lam[:, 0], nu=1.5 if kernel_id == orc.MATERN32 else 2.5)
+    gpr = GaussianProcessRegressor(kernel=ConstantKernel(alpha[0] ** 2, "fixed") * base, alpha=sigma[0] ** 2, optimizer=None).fit(X.T, Y[0])
+    m_sk, s_sk = gpr.predict(Xq.T, return_std=True)
+    np.testing.assert_allclose(mu[0], m_sk, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(var[0], s_sk ** 2, rtol=1e-7, atol=1e-10 * alpha[0] ** 2)
