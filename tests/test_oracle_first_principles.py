@@ -113,3 +113,18 @@ def test_gp_predict_against_sklearn(kernel_id):
     m_sk, s_sk = gpr.predict(Xq.T, return_std=True)
     np.testing.assert_allclose(mu[0], m_sk, rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(var[0], s_sk ** 2, rtol=1e-7, atol=1e-10 * alpha[0] ** 2)
+
+
+def test_mmd_against_gaussian_closed_form():
+    """calc_mmd (src/metrics/mmd.jl:23-28) on samples of two isotropic Gaussians against the population value: for the SE kernel
+    E k(x, y) = prod_k lam_k / sqrt(lam_k^2 + s1^2 + s2^2) * exp(-(m1 - m2)^2 / (2 (lam_k^2 + s1^2 + s2^2))).  The V-statistic
+    includes the n + m unit diagonal terms, which the expectation below accounts for."""
+    rng = np.random.default_rng(0)
+    d, n, m = 2, 12000, 10000
+    lam = np.array([1.0, 1.5]); m1, s1, m2, s2 = 0.0, 1.0, 0.4, 1.2
+    A = m1 + s1 * rng.standard_normal((d, n)); B = m2 + s2 * rng.standard_normal((d, m))
+    ek = lambda dm, sa, sb: float(np.prod(lam / np.sqrt(lam ** 2 + sa ** 2 + sb ** 2) * np.exp(-dm ** 2 / (2 * (lam ** 2 + sa ** 2 + sb ** 2)))))
+    exx, eyy, exy = ek(0.0, s1, s1), ek(0.0, s2, s2), ek(m1 - m2, s1, s2)
+    expected = (exx * (n - 1) / n + 1.0 / n) + (eyy * (m - 1) / m + 1.0 / m) - 2.0 * exy
+    got = orc.calc_mmd(orc.SE, lam, A, B)[0]
+    assert got == pytest.approx(expected, abs=6e-3) and expected > 0.03          # sampling noise of the estimate is ~2e-3 here
