@@ -217,3 +217,22 @@ def test_confidence_set_host_logic_matches_oracle(bb):
     assert bb.set_iou(in_a, in_b, lp) == pytest.approx(orc.set_iou(in_a, in_b, np.exp(lp)), rel=1e-12)
     assert bb.set_iou(in_a, in_a, lp) == pytest.approx(1.0, rel=1e-14)
     assert np.isnan(bb.weighted_quantile(np.array([1.0, np.nan]), np.ones(2), 0.5))
+
+
+def test_product_prior_host_methods(bb):
+    """ProductPrior.logpdf / rand run on the host (the device epilogue applies the same formulas inside the sweep): against the
+    oracle and scipy.stats, support handling included."""
+    from oracle import bosip_oracle as orc
+    kinds = [bb.UNIFORM, bb.NORMAL, bb.TRUNCNORMAL]
+    prm = [(-5.0, 5.0), (0.3, 1.7), (0.0, 5.0 / 3.0, -5.0, 5.0)]
+    prior = bb.ProductPrior(kinds, prm)
+    rng = np.random.default_rng(2)
+    X = rng.uniform(-6, 6, (3, 300)); X[:, 0] = [-5.0, 0.0, 5.0]
+    o = orc.log_prior(orc.ProductPrior(kinds, prm), X)
+    g = prior.logpdf(X)
+    fin = np.isfinite(o)
+    assert np.array_equal(np.isfinite(g), fin) and fin[0]
+    np.testing.assert_allclose(g[fin], o[fin], rtol=1e-13, atol=1e-13)
+    S = prior.rand(20000, rng)
+    assert S.shape == (3, 20000) and np.all(np.isfinite(prior.logpdf(S)))            # every draw lies in the support
+    assert abs(S[1].mean() - 0.3) < 0.05 and abs(S[2].std() - 5.0 / 3.0) < 0.06        # truncation at 3 sigma barely changes the spread
