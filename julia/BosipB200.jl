@@ -9,7 +9,7 @@
 #   4. calc_mmd / calc_tv methods                      -> metrics
 module BosipB200
 
-using BOSIP, BOSS, Distributions
+using BOSIP, BOSS, Distributions, LinearAlgebra
 
 const LIB = get(ENV, "BOSIP_B200_LIB", joinpath(@__DIR__, "..", "bosip.jl_b200", "libbosip_b200.so"))
 
