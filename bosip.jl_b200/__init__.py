@@ -13,10 +13,11 @@ from .api import (B200CandidateAM, B200GPPosterior, BosipB200Error, BosipProblem
                   log_posterior_mean, log_posterior_variance, model_posterior, model_posterior_from_factors,
                   posterior_eval, posterior_mean, posterior_variance, normal_likelihood_eval, loglike, loglike_marginal,
                   log_approx_marginal_likelihood, log_marginal_likelihood_mean, log_sq_likelihood_mean, compute_marginals_int,
-                  generate_LHC, normalize_prob_vals, LogNormalLikelihood, NormalDiffLikelihood, NormalSumLikelihood, ExpLikelihood, bosip, DataLimit, IterLimit)
+                  generate_LHC, normalize_prob_vals, MultiContext, MultiGPPosterior, model_posterior_multi, posterior_eval_multi,
+                  acq_argmax_multi, evidence_multi, LogNormalLikelihood, NormalDiffLikelihood, NormalSumLikelihood, ExpLikelihood, bosip, DataLimit, IterLimit)
 
 from .sampling import (AEConfidence, AMIS, AMISSampler, AnalyticalFitter, NormalProposal, OptMMDMetric, amis_log_weights,  # noqa: F401,E402
-                       approx_cutoff_area, exp_weights, find_cutoff, mixture_pdf_sum, resample, sample_posterior,
+                       approx_cutoff_area, confidence_iou, exp_weights, find_cutoff, mixture_pdf_sum, resample, sample_posterior,
                        sample_posterior_pure, set_iou, weighted_moments, weighted_quantile)
 
 __version__ = "0.1.0"

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "bosip_b200_shutdown": (C.c_int, [C.c_void_p]),
     "bosip_b200_last_error": (C.c_char_p, [C.c_void_p]),
     "bosip_b200_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bosip_b200_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bosip_b200_i8_issuers": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "bosip_b200_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
     "bosip_b200_set_chunk": (C.c_int, [C.c_void_p, C.c_int64]),
     "bosip_b200_set_variance_engine": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -61,6 +63,26 @@ PROTOTYPES = {
                                              C.POINTER(C.c_void_p)]),
     "bosip_b200_gp_get_factors": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "bosip_b200_gp_free": (C.c_int, [C.c_void_p]),
+    "bosip_b200_gp_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bosip_b200_init_multi": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "bosip_b200_shutdown_multi": (C.c_int, [C.c_void_p]),
+    "bosip_b200_multi_size": (C.c_int, [C.c_void_p]),
+    "bosip_b200_multi_context": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "bosip_b200_gp_multi_replica": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "bosip_b200_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "bosip_b200_gp_fit_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
+                                          c_double_p, c_double_p, c_double_p, C.POINTER(GpOpts), C.POINTER(C.c_void_p)]),
+    "bosip_b200_gp_free_multi": (C.c_int, [C.c_void_p]),
+    "bosip_b200_posterior_eval_multi": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64, C.c_void_p,
+                                                  C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p, C.c_int, C.c_int64, c_int64_p,
+                                                  c_double_p]),
+    "bosip_b200_acq_argmax_multi": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.POINTER(CandSrc), C.c_int64,
+                                              C.c_int64, C.c_int, c_int64_p, c_double_p, c_double_p]),
+    "bosip_b200_evidence_sum_multi": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64, C.c_uint,
+                                                c_double_p]),
+    "bosip_b200_mmd_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                       c_double_p]),
+    "bosip_b200_tv_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, c_double_p]),
     "bosip_b200_gp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bosip_b200_posterior_eval": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
                                             C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, c_int64_p]),
@@ -75,6 +97,10 @@ PROTOTYPES = {
                                                     C.c_void_p, c_int64_p]),
     "bosip_b200_acq_argmax": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), C.POINTER(CandSrc), C.c_int64,
                                         C.c_int64, C.c_int, c_int64_p, c_double_p, c_double_p]),
+    "bosip_b200_acq_argmax_bi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(LikeNormal), C.POINTER(Prior), C.POINTER(CandSrc),
+                                           C.c_int64, C.c_int64, C.c_int, c_int64_p, c_double_p, c_double_p]),
+    "bosip_b200_evidence_sum_bi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(LikeNormal), C.POINTER(Prior), C.c_void_p, C.c_int64,
+                                             C.c_int, C.c_uint, c_double_p]),
     "bosip_b200_marginals_int": (C.c_int, [C.c_void_p, C.POINTER(LikeNormal), C.POINTER(Prior), c_double_p, C.c_int64, C.c_int,
                                            c_double_p, c_double_p, C.c_uint, c_double_p, c_double_p]),
     "bosip_b200_candidates": (C.c_int, [C.c_void_p, C.POINTER(CandSrc), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
@@ -96,6 +122,11 @@ PROTOTYPES = {
                                               c_double_p, C.c_void_p]),
     "bosip_b200_resample": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p,
                                       C.c_void_p]),
+    "bosip_b200_weighted_quantile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, c_double_p]),
+    "bosip_b200_cutoff_area": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, c_double_p]),
+    "bosip_b200_set_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "bosip_b200_confidence_iou": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, c_double_p,
+                                            c_double_p, c_double_p]),
     "bosip_b200_fp64_peak": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "bosip_b200_math_selftest": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
     "bosip_b200_timing_reset": (C.c_int, [C.c_void_p, C.c_int]),

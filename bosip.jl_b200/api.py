@@ -120,6 +120,20 @@ class Context:
         """Launch compute kernels on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); None restores."""
         self._check(self.lib.bosip_b200_set_stream(self.h, cuda_stream))
 
+    def order_after_torch(self):
+        """Order the compute stream after torch's CURRENT stream on this device.  Every call that hands device pointers to the
+        library goes through this first: the tensors may still be being written (a `.t().contiguous()` copy, `torch.zeros`,
+        `copy_()`), or their memory may have been recycled by torch's caching allocator while earlier torch kernels that use it
+        are still queued -- the library's own streams are non-blocking and see none of that implicitly."""
+        import torch
+        self._check(self.lib.bosip_b200_stream_wait(self.h, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def i8_issuers(self) -> int:
+        """MMA-issuing threads of the INT8 engine: 2 after the bitwise self-check passed, 1 after a mismatch, 0 before the first INT8 launch."""
+        n = C.c_int()
+        self._check(self.lib.bosip_b200_i8_issuers(self.h, C.byref(n)))
+        return n.value
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self._check(self.lib.bosip_b200_launch_count(self.h, C.byref(n)))
@@ -409,6 +423,8 @@ class B200GPPosterior:
             raise NotImplementedError("a prior mean function needs host inputs")
         mu, mu_p = _out((self.p, M), mem, keep) if want_mu else (None, None)
         var, var_p = _out((self.p, M), mem, keep) if want_var else (None, None)
+        if mem == L.DEVICE:
+            self.ctx.order_after_torch()
         self.ctx._check(self.ctx.lib.bosip_b200_gp_predict(self.h, addr, M, mem, maddr, mu_p, var_p))
         if vec:
             mu = mu[:, 0] if mu is not None else None
@@ -480,6 +496,13 @@ def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optiona
     vec = (np.ndim(X) == 1) if not _is_torch(X) else (X.dim() == 1)
     Xm = X.reshape(post.d, 1) if vec else X
     keep, addr, mem, M = _colmajor(Xm, post.d)
+    models = [q.model for q in (ensemble or [post])]
+    if any(m.mean is not None for m in models):
+        # the C ABI takes ONE p x M array of prior-mean values, evaluated on the host
+        if mem == L.DEVICE:
+            raise NotImplementedError("a prior mean function needs host inputs (the mean is a host callable)")
+        if any(m.mean is not models[0].mean for m in models):
+            raise NotImplementedError("hyper-parameter samples with different prior mean functions are not supported")
     mkeep, maddr = post._mean_at(Xm) if mem == L.HOST else (None, None)
     lk = like._c()
     lp_keep = lp_addr = None
@@ -503,6 +526,8 @@ def posterior_eval(post: B200GPPosterior, like: NormalLikelihood, prior: Optiona
         else:
             ptrs.append(None)
     ncl = C.c_int64(0); bi = C.c_int64(-1); bv = C.c_double(0.0)
+    if mem == L.DEVICE:
+        post.ctx.order_after_torch()
     if ensemble is None:
         post.ctx._check(post.ctx.lib.bosip_b200_posterior_eval_argmax(
             post.h, C.byref(lk), C.byref(pr), addr, M, mem, maddr, want, ptrs[0], ptrs[1], ptrs[2], C.byref(ncl),
@@ -553,6 +578,8 @@ def normal_likelihood_eval(like: NormalLikelihood, mu, var=None, outputs=_LIKE_O
         else:
             ptrs.append(None)
     ncl = C.c_int64(0); lk = like._c()
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
     ctx._check(ctx.lib.bosip_b200_normal_likelihood_eval(ctx.h, C.byref(lk), pmu, pvar, M, mem, *ptrs, C.byref(ncl)))
     if vec:
         res = {k: (v[:, 0] if v.ndim == 2 else float(v[0])) for k, v in res.items()}
@@ -638,13 +665,20 @@ def _exp(v):
 def evidence(bosip: BosipProblem, which: str = "approx", xs=None, samples: int = 10_000, rng=None) -> float:
     """evidence(post, x_prior; xs, samples) -- src/posterior/evidence.jl:19-24: mean_i post(x_i)/pdf(prior, x_i)."""
     post = bosip.model_posterior()
+    ensemble = list(post) if isinstance(post, (list, tuple)) else [post]     # MultiFittedParams: averaged in linear space
+    post = ensemble[0]
+    if any(q.model.mean is not None for q in ensemble):
+        raise NotImplementedError("evidence with a prior mean function is not wired through the fused sweep")
     if xs is None:
         xs = bosip.x_prior.rand(samples, rng or np.random.default_rng())
     keep, addr, mem, S = _colmajor(xs, post.d)
     lk = bosip.likelihood._c(); pr = bosip.x_prior._c()
     out = C.c_double()
     w = L.WANT_APPROX if which == "approx" else L.WANT_MEAN
-    post.ctx._check(post.ctx.lib.bosip_b200_evidence_sum(post.h, C.byref(lk), C.byref(pr), addr, S, mem, w, C.byref(out)))
+    if mem == L.DEVICE:
+        post.ctx.order_after_torch()
+    hs = (C.c_void_p * len(ensemble))(*[q.h for q in ensemble])
+    post.ctx._check(post.ctx.lib.bosip_b200_evidence_sum_bi(hs, len(ensemble), C.byref(lk), C.byref(pr), addr, S, mem, w, C.byref(out)))
     return out.value / S
 
 
@@ -721,19 +755,26 @@ class CandidateSource:
 
 def acq_argmax(post: B200GPPosterior, like, prior, acq, src: CandidateSource, start: int = 0, count: Optional[int] = None):
     """Fused evaluate + argmax over candidates start..start+count-1 of `src`.  Returns (global index, value, x)."""
+    ensemble = list(post) if isinstance(post, (list, tuple)) else [post]     # MultiFittedParams
+    post = ensemble[0]
+    if any(q.model.mean is not None for q in ensemble):
+        raise NotImplementedError("acq_argmax with a prior mean function: evaluate posterior_eval(..., acq=...) on explicit host points")
     count = src.count - start if count is None else count
     cs = L.CandSrc(); cs.kind = src.kind; keep = None
     if src.kind == L.CAND_POINTS:
         pts = src.points[:, start:start + count]
         keep, addr, mem, _ = _colmajor(pts, post.d)
         cs.points = addr; cs.mem = mem
+        if mem == L.DEVICE:
+            post.ctx.order_after_torch()
     else:
         cs.seed = src.seed; cs.lb = _dptr(src.lb); cs.ub = _dptr(src.ub); cs.n_per_dim = src.n_per_dim
     lk = like._c(); pr = prior._c() if prior is not None else L.Prior(post.d, None, None, None)
     bi, bv = C.c_int64(-1), C.c_double()
     bx = np.full(post.d, np.nan)
-    post.ctx._check(post.ctx.lib.bosip_b200_acq_argmax(post.h, C.byref(lk), C.byref(pr), C.byref(cs), count, start, acq.acq_id,
-                                                      C.byref(bi), C.byref(bv), _dptr(bx)))
+    hs = (C.c_void_p * len(ensemble))(*[q.h for q in ensemble])
+    post.ctx._check(post.ctx.lib.bosip_b200_acq_argmax_bi(hs, len(ensemble), C.byref(lk), C.byref(pr), C.byref(cs), count, start, acq.acq_id,
+                                                         C.byref(bi), C.byref(bv), _dptr(bx)))
     return bi.value, bv.value, bx
 
 
@@ -751,6 +792,8 @@ class B200CandidateAM:
         start, count = parallel.shard_range(self.source.count)
         idx, val, x = acq_argmax(post, bosip.likelihood, bosip.x_prior, acq, self.source, start, count)
         idx, val, x = parallel.argmax_allgather(idx, val, x)
+        if idx < 0:
+            raise ValueError("maximize_acquisition: the candidate set is empty")
         return x, val
 
 
@@ -759,6 +802,7 @@ def candidates(ctx: Context, src: CandidateSource, start: int, count: int, devic
     d = len(src.lb)
     cs = L.CandSrc(); cs.kind = src.kind; cs.seed = src.seed; cs.lb = _dptr(src.lb); cs.ub = _dptr(src.ub); cs.n_per_dim = src.n_per_dim
     if device_out is not None:
+        ctx.order_after_torch()
         ctx._check(ctx.lib.bosip_b200_candidates(ctx.h, C.byref(cs), d, count, start, L.DEVICE, device_out.data_ptr()))
         return device_out
     out = np.empty((d, count), order="F")
@@ -787,6 +831,8 @@ def calc_mmd(kernel: Kernel, X, Y, ctx: Optional[Context] = None) -> float:
         raise ValueError("X and Y must live in the same memory space")
     sums = np.zeros(3)
     rank, world = parallel.rank_world()
+    if mema == L.DEVICE:
+        ctx.order_after_torch()
     ctx._check(ctx.lib.bosip_b200_mmd_sums(ctx.h, kernel.kernel, d, _dptr(lam), pa, n, pb, m, mema, rank, world, _dptr(sums)))
     sums = parallel.allreduce_sum(sums)
     return float(sums[0] / (n * n) + sums[1] / (m * m) - 2.0 * sums[2] / (n * m))
@@ -812,6 +858,8 @@ def calc_tv(log_ws, approx_logvals, true_logvals, ctx: Optional[Context] = None)
     kw, pw, mem, G = _colmajor(log_ws); ka, pa, m2, _ = _colmajor(approx_logvals); kt, pt, m3, _ = _colmajor(true_logvals)
     if not (mem == m2 == m3):
         raise ValueError("inputs must live in the same memory space")
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
     if parallel.rank_world()[1] == 1:      # one GPU: both stages in one call, host vectors uploaded once
         out = np.zeros(1)
         ctx._check(ctx.lib.bosip_b200_tv(ctx.h, pw, pa, pt, G, mem, _dptr(out)))
@@ -965,3 +1013,155 @@ def bosip(problem: BosipProblem, simulator: Callable, acquisition=None, acq_maxi
         if callback is not None:
             callback(problem, it, x, val)
     return problem
+
+
+# ----------------------------------------------------------------------------------------------- multi-GPU behind the C ABI
+class _BorrowedContext(Context):
+    """A per-device context owned by a MultiContext (never shut down on its own)."""
+
+    def __init__(self, lib, handle, device):   # noqa: super().__init__ would create a new context
+        self.lib, self.h, self.device = lib, C.c_void_p(handle), device
+
+    def close(self):
+        self.h = None
+
+
+class MultiContext:
+    """bosip_b200_init_multi: ONE host process driving several GPUs through the C ABI -- what a Julia host gets without torchrun
+    (include/bosip_b200.h, csrc/multi.cu).  Points are sharded into contiguous ranges, one host thread per device, results
+    combined in rank order inside the library.  Large buffers are host arrays."""
+
+    def __init__(self, devices):
+        self.lib = L.load()
+        devs = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        rc = self.lib.bosip_b200_init_multi(len(devs), arr, C.byref(h))
+        if rc != 0:
+            raise BosipB200Error(rc, (self.lib.bosip_b200_multi_last_error(None) or b"").decode())
+        self.h, self.devices = h, devs
+
+    @property
+    def size(self) -> int:
+        return self.lib.bosip_b200_multi_size(self.h)
+
+    def context(self, rank: int) -> Context:
+        return _BorrowedContext(self.lib, self.lib.bosip_b200_multi_context(self.h, rank), self.devices[rank])
+
+    def _check(self, rc: int):
+        if rc == 0:
+            return
+        msg = (self.lib.bosip_b200_multi_last_error(self.h) or b"").decode()
+        if rc == L.EDOMAIN:
+            raise DomainError(rc, msg)
+        if rc == L.ENOTPD:
+            raise PosDefException(rc, msg)
+        raise BosipB200Error(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bosip_b200_shutdown_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- metrics (src/metrics/mmd.jl:23-28, tv.jl:59-73)
+    def calc_mmd(self, kernel: "Kernel", X, Y) -> float:
+        lam = np.ascontiguousarray(kernel.lengthscales, dtype=np.float64)
+        ka, pa, ma, n = _colmajor(np.asarray(X), len(lam)); kb, pb, mb, m = _colmajor(np.asarray(Y), len(lam))
+        out = C.c_double()
+        self._check(self.lib.bosip_b200_mmd_multi(self.h, kernel.kernel, len(lam), _dptr(lam), pa, n, pb, m, C.byref(out)))
+        return out.value
+
+    def calc_tv(self, log_ws, approx_logvals, true_logvals) -> float:
+        kw, pw, _, G = _colmajor(np.asarray(log_ws)); ka, pa, _, _ = _colmajor(np.asarray(approx_logvals)); kt, pt, _, _ = _colmajor(np.asarray(true_logvals))
+        out = C.c_double()
+        self._check(self.lib.bosip_b200_tv_multi(self.h, pw, pa, pt, G, C.byref(out)))
+        return out.value
+
+
+class MultiGPPosterior:
+    """N replicas of one conditioned GP (bosip_b200_gp_fit_multi)."""
+
+    def __init__(self, mctx: MultiContext, handle, model: GaussianProcess, d: int, N: int, p: int):
+        self.mctx, self.h, self.model, self.d, self.N, self.p = mctx, handle, model, d, N, p
+
+    def free(self):
+        if self.h:
+            self.mctx.lib.bosip_b200_gp_free_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def model_posterior_multi(model: GaussianProcess, X, Y, mctx: MultiContext) -> MultiGPPosterior:
+    X = np.asfortranarray(np.asarray(X, dtype=np.float64)); Y = np.asfortranarray(np.asarray(Y, dtype=np.float64))
+    d, N = X.shape; p = Y.shape[0]
+    lam = np.asfortranarray(np.asarray(model.lengthscales, dtype=np.float64).reshape(d, p))
+    alpha = np.ascontiguousarray(model.amplitudes, dtype=np.float64); sigma = np.ascontiguousarray(model.noise_std, dtype=np.float64)
+    if model.mean is not None:
+        raise NotImplementedError("the multi-GPU entry points take a zero prior mean")
+    h = C.c_void_p(); o = _opts(model)
+    mctx._check(mctx.lib.bosip_b200_gp_fit_multi(mctx.h, model.kernel, d, N, p, _dptr(X), _dptr(Y), _dptr(lam), _dptr(alpha), _dptr(sigma),
+                                                 None, C.byref(o), C.byref(h)))
+    return MultiGPPosterior(mctx, h, model, d, N, p)
+
+
+def posterior_eval_multi(post: MultiGPPosterior, like, prior: Optional[ProductPrior], X, want: int, logprior=None, acq=None,
+                         index_offset: int = 0, out=None):
+    """posterior_eval through bosip_b200_posterior_eval_multi: host X (d x M) sharded over the devices of `post.mctx`."""
+    keep, addr, mem, M = _colmajor(np.asarray(X), post.d)
+    lk = like._c()
+    lp_keep = lp_addr = None
+    if logprior is not None:
+        lp_keep, lp_addr, _, _ = _colmajor(np.asarray(logprior))
+    pr = prior._c(lp_addr) if prior is not None else L.Prior(post.d, None, None, lp_addr)
+    outs, ptrs = {}, []
+    for bit, name in ((L.WANT_APPROX, "log_approx_post"), (L.WANT_MEAN, "log_post_mean"), (L.WANT_VAR, "log_post_var")):
+        if want & bit:
+            o = out[name] if (out is not None and name in out) else np.empty(M)
+            outs[name] = o; ptrs.append(o.ctypes.data)
+        else:
+            ptrs.append(None)
+    ncl = C.c_int64(0); bi = C.c_int64(-1); bv = C.c_double(0.0)
+    post.mctx._check(post.mctx.lib.bosip_b200_posterior_eval_multi(
+        post.h, C.byref(lk), C.byref(pr), addr, M, None, want, ptrs[0], ptrs[1], ptrs[2], C.byref(ncl),
+        acq.acq_id if acq is not None else -1, index_offset, C.byref(bi), C.byref(bv)))
+    outs["n_clamped"] = ncl.value
+    if acq is not None:
+        outs["best_idx"], outs["best_val"] = bi.value, bv.value
+    return outs
+
+
+def acq_argmax_multi(post: MultiGPPosterior, like, prior, acq, src: CandidateSource, start: int = 0, count: Optional[int] = None):
+    """Fused evaluate + argmax over candidates start..start+count-1 of `src`, sharded over the devices inside the library."""
+    count = src.count - start if count is None else count
+    cs = L.CandSrc(); cs.kind = src.kind; keep = None
+    if src.kind == L.CAND_POINTS:
+        keep, addr, mem, _ = _colmajor(np.asarray(src.points)[:, start:start + count], post.d)
+        cs.points = addr; cs.mem = L.HOST
+    else:
+        cs.seed = src.seed; cs.lb = _dptr(src.lb); cs.ub = _dptr(src.ub); cs.n_per_dim = src.n_per_dim
+    lk = like._c(); pr = prior._c() if prior is not None else L.Prior(post.d, None, None, None)
+    bi, bv = C.c_int64(-1), C.c_double()
+    bx = np.full(post.d, np.nan)
+    post.mctx._check(post.mctx.lib.bosip_b200_acq_argmax_multi(post.h, C.byref(lk), C.byref(pr), C.byref(cs), count, start, acq.acq_id,
+                                                               C.byref(bi), C.byref(bv), _dptr(bx)))
+    return bi.value, bv.value, bx
+
+
+def evidence_multi(post: MultiGPPosterior, like, prior: ProductPrior, xs, which: str = "approx") -> float:
+    keep, addr, mem, S = _colmajor(np.asarray(xs), post.d)
+    lk = like._c(); pr = prior._c()
+    out = C.c_double()
+    post.mctx._check(post.mctx.lib.bosip_b200_evidence_sum_multi(post.h, C.byref(lk), C.byref(pr), addr, S,
+                                                                 L.WANT_APPROX if which == "approx" else L.WANT_MEAN, C.byref(out)))
+    return out.value / S

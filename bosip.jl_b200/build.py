@@ -17,7 +17,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libbosip_b200.so")
 # (source, object stem, extra flags): kstar.cu is compiled once per kernel family, its 165 template instantiations dominate the build
 SOURCES = [("kstar.cu", f"kstar_k{k}", [f"-DKSTAR_KERNEL_ID={k}"]) for k in range(3)] + [
-    (f, f[:-3], []) for f in ("api.cu", "vargemm.cu", "vargemm_i8.cu", "epilogue.cu", "fit.cu", "metrics.cu", "sampler.cu", "peaks.cu")]
+    (f, f[:-3], []) for f in ("api.cu", "vargemm.cu", "vargemm_i8.cu", "epilogue.cu", "fit.cu", "metrics.cu", "sampler.cu", "peaks.cu", "multi.cu", "confset.cu")]
 HEADERS = ["common.cuh", "philox.cuh", "fastmath.cuh", os.path.join("..", "..", "include", "bosip_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -368,6 +368,23 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   return 0;
 }
 
+// Fill sw.gp / sw.ep (one fit) or sw.fits / sw.fit_ep (BI ensemble of hyper-parameter samples).
+static int set_fits(Ctx* ctx, Sweep& sw, bosip_b200_gp* const* gps, int n, const bosip_b200_like_normal* like, const bosip_b200_prior* prior) {
+  sw.gp = gps[0]->g;
+  if (n == 1) return make_epi(ctx, sw.gp, like, prior, &sw.ep);
+  for (int f = 0; f < n; ++f) {
+    if (!gps[f] || !gps[f]->g) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "NULL GP handle in the ensemble");
+    Gp* g = gps[f]->g;
+    if (g->ctx != sw.gp->ctx || g->d != sw.gp->d || g->p != sw.gp->p || g->N != sw.gp->N || g->kernel_id != sw.gp->kernel_id)
+      BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "all hyper-parameter samples must share context, kernel, d, p and N");
+    EpiParams e;
+    BOSIP_TRY(make_epi(ctx, g, like, prior, &e));
+    sw.fits.push_back(g); sw.fit_ep.push_back(e);
+  }
+  sw.ep = sw.fit_ep[0];  // carries the prior for bi_finish
+  return 0;
+}
+
 }  // namespace bosip
 
 using namespace bosip;
@@ -420,7 +437,8 @@ int bosip_b200_init(int device, bosip_b200_ctx** out) {
     ok = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_comp[b], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreate(&ctx->ev_t0) == cudaSuccess && cudaEventCreate(&ctx->ev_t1) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev_t0) == cudaSuccess && cudaEventCreate(&ctx->ev_t1) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->ev_dep, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { g_init_error = "failed to create CUDA streams/events"; delete h; return BOSIP_B200_ECUDA; }
   *out = h;
   return 0;
@@ -434,7 +452,7 @@ int bosip_b200_shutdown(bosip_b200_ctx* h) {
   if (ctx->ws) cudaFree(ctx->ws);
   for (auto& e : h->tp.pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_in[b]); cudaEventDestroy(ctx->ev_comp[b]); cudaEventDestroy(ctx->ev_out[b]); }
-  cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+  cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1); cudaEventDestroy(ctx->ev_dep);
   cudaStreamDestroy(ctx->s_own); cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out);
   delete h;
   return 0;
@@ -444,6 +462,22 @@ int bosip_b200_set_stream(bosip_b200_ctx* h, void* stream) {
   API_LOCK(h);
   BOSIP_CUDA(ctx, cudaStreamSynchronize(ctx->s_comp));
   ctx->s_comp = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->s_own;
+  return 0;
+}
+
+int bosip_b200_stream_wait(bosip_b200_ctx* h, void* producer) {
+  API_LOCK(h);
+  cudaStream_t ps = reinterpret_cast<cudaStream_t>(producer);
+  if (ps == ctx->s_comp) return 0;   // same stream: already ordered
+  BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_dep, ps));
+  BOSIP_CUDA(ctx, cudaStreamWaitEvent(ctx->s_comp, ctx->ev_dep, 0));
+  return 0;
+}
+
+int bosip_b200_i8_issuers(bosip_b200_ctx* h, int* out) {
+  API_LOCK(h);
+  if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
+  *out = ctx->i8_issuers;
   return 0;
 }
 
@@ -505,6 +539,14 @@ int bosip_b200_gp_get_factors(bosip_b200_gp* gh, double* L, double* Linv, double
   if (L) BOSIP_CUDA(ctx, cudaMemcpy(L, gp->L, nn, cudaMemcpyDeviceToHost));
   if (Linv) BOSIP_CUDA(ctx, cudaMemcpy(Linv, gp->Linv, nn, cudaMemcpyDeviceToHost));
   if (a) BOSIP_CUDA(ctx, cudaMemcpy(a, gp->a, (size_t)gp->p * gp->N * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bosip_b200_gp_dims(const bosip_b200_gp* gh, int* d, int* N, int* p) {
+  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+  if (d) *d = gh->g->d;
+  if (N) *N = gh->g->N;
+  if (p) *p = gh->g->p;
   return 0;
 }
 
@@ -588,16 +630,7 @@ int bosip_b200_posterior_eval_bi(bosip_b200_gp* const* gps, int n_samples, const
   sw.lv = (want & BOSIP_B200_WANT_VAR) ? log_post_var : nullptr;
   sw.need_var = do_arg || (want & (BOSIP_B200_WANT_MEAN | BOSIP_B200_WANT_VAR)) != 0;
   sw.do_argmax = do_arg; sw.exp_vals = (acq == BOSIP_B200_ACQ_MAXVAR) ? 1 : 0; sw.index_offset = index_offset;
-  for (int f = 0; f < n_samples; ++f) {
-    if (!gps[f] || !gps[f]->g) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "NULL GP handle in the ensemble");
-    Gp* g = gps[f]->g;
-    if (g->ctx != sw.gp->ctx || g->d != sw.gp->d || g->p != sw.gp->p || g->N != sw.gp->N || g->kernel_id != sw.gp->kernel_id)
-      BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "all hyper-parameter samples must share context, kernel, d, p and N");
-    EpiParams e;
-    BOSIP_TRY(make_epi(ctx, g, like, prior, &e));
-    sw.fits.push_back(g); sw.fit_ep.push_back(e);
-  }
-  sw.ep = sw.fit_ep[0];  // carries the prior for bi_finish
+  BOSIP_TRY(set_fits(ctx, sw, gps, n_samples, like, prior));
   if (prior && prior->logprior) sw.logprior = prior->logprior;
   int rc = run_sweep(ctx, sw);
   if (n_clamped) *n_clamped = sw.n_clamped;
@@ -670,17 +703,18 @@ int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* h, const bosip_b200_like_n
   return 0;
 }
 
-int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
-                          const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
-                          double* best_val, double* best_x) {
-  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
+static int acq_argmax_common(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                             const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
+                             double* best_val, double* best_x) {
+  if (!gps || n_samples < 1 || !gps[0] || !gps[0]->g) return BOSIP_B200_EINVAL;
+  bosip_b200_gp* gh = gps[0];
   bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
   API_LOCK(h);
   if (!like || !src || !best_idx || !best_val) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null argument");
   if (acq != BOSIP_B200_ACQ_MAXVAR && acq != BOSIP_B200_ACQ_LOGMAXVAR) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown acquisition");
   if (index_offset < 0) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "index_offset must be >= 0");
   Sweep sw;
-  sw.gp = gh->g; sw.M = M; sw.index_offset = index_offset; sw.use_like = true; sw.need_var = true;
+  sw.M = M; sw.index_offset = index_offset; sw.use_like = true; sw.need_var = true;
   sw.do_argmax = true; sw.exp_vals = (acq == BOSIP_B200_ACQ_MAXVAR) ? 1 : 0;
   bosip_b200_cand_src shifted = *src;
   if (src->kind == BOSIP_B200_CAND_POINTS) {
@@ -694,7 +728,7 @@ int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like,
   } else {
     BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown candidate source kind");
   }
-  BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
+  BOSIP_TRY(set_fits(ctx, sw, gps, n_samples, like, prior));
   BOSIP_TRY(run_sweep(ctx, sw));
   *best_idx = sw.best_idx;
   *best_val = sw.best_idx >= 0 ? sw.best_val : -INFINITY;
@@ -712,6 +746,18 @@ int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like,
     }
   }
   return 0;
+}
+
+int bosip_b200_acq_argmax(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                          const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
+                          double* best_val, double* best_x) {
+  return acq_argmax_common(&gh, 1, like, prior, src, M, index_offset, acq, best_idx, best_val, best_x);
+}
+
+int bosip_b200_acq_argmax_bi(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                             const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
+                             double* best_val, double* best_x) {
+  return acq_argmax_common(gps, n_samples, like, prior, src, M, index_offset, acq, best_idx, best_val, best_x);
 }
 
 int bosip_b200_marginals_int(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior, const double* lhc,
@@ -764,22 +810,32 @@ int bosip_b200_candidates(bosip_b200_ctx* h, const bosip_b200_cand_src* src, int
   return 0;
 }
 
-int bosip_b200_evidence_sum(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
-                            const double* xs, int64_t S, int mem, unsigned which, double* sum_out) {
-  if (!gh || !gh->g) return BOSIP_B200_EINVAL;
-  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
+static int evidence_sum_common(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                               const double* xs, int64_t S, int mem, unsigned which, double* sum_out) {
+  if (!gps || n_samples < 1 || !gps[0] || !gps[0]->g) return BOSIP_B200_EINVAL;
+  bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gps[0]->g->ctx);
   API_LOCK(h);
   if (!like || !prior || !xs || !sum_out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null argument");
   if (which != BOSIP_B200_WANT_APPROX && which != BOSIP_B200_WANT_MEAN) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "which must be WANT_APPROX or WANT_MEAN");
   Sweep sw;
-  sw.gp = gh->g; sw.mem = mem; sw.xq = xs; sw.M = S; sw.use_like = true;
+  sw.mem = mem; sw.xq = xs; sw.M = S; sw.use_like = true;
   sw.need_var = (which == BOSIP_B200_WANT_MEAN);
   sw.do_evidence = true; sw.evid_which = which;
-  BOSIP_TRY(make_epi(ctx, gh->g, like, prior, &sw.ep));
+  BOSIP_TRY(set_fits(ctx, sw, gps, n_samples, like, prior));
   if (prior->logprior) sw.logprior = prior->logprior;
   BOSIP_TRY(run_sweep(ctx, sw));
   *sum_out = sw.evid_sum;
   return 0;
+}
+
+int bosip_b200_evidence_sum(bosip_b200_gp* gh, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                            const double* xs, int64_t S, int mem, unsigned which, double* sum_out) {
+  return evidence_sum_common(&gh, 1, like, prior, xs, S, mem, which, sum_out);
+}
+
+int bosip_b200_evidence_sum_bi(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                               const double* xs, int64_t S, int mem, unsigned which, double* sum_out) {
+  return evidence_sum_common(gps, n_samples, like, prior, xs, S, mem, which, sum_out);
 }
 
 int bosip_b200_mmd_sums(bosip_b200_ctx* h, int kernel_id, int d, const double* lambda, const double* A, int64_t n,
@@ -845,6 +901,24 @@ int bosip_b200_resample(bosip_b200_ctx* h, int d, const double* X, const double*
   API_LOCK(h);
   if (!X || !ws || !out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "resample: NULL argument");
   return resample(ctx, d, X, ws, M, seed, count, mem, out, idx);
+}
+
+int bosip_b200_weighted_quantile(bosip_b200_ctx* h, const double* vals, const double* ws, int64_t n, int mem, double p, double* out) {
+  API_LOCK(h);
+  return cs_weighted_quantile(ctx, vals, ws, n, mem, p, out);
+}
+int bosip_b200_cutoff_area(bosip_b200_ctx* h, const double* vals, const double* ws, int64_t n, int mem, double c, double* out) {
+  API_LOCK(h);
+  return cs_cutoff_area(ctx, vals, ws, n, mem, c, out);
+}
+int bosip_b200_set_iou(bosip_b200_ctx* h, const uint8_t* in_A, const uint8_t* in_B, const double* logprior, int64_t n, int mem, double* out) {
+  API_LOCK(h);
+  return cs_set_iou(ctx, in_A, in_B, logprior, n, mem, out);
+}
+int bosip_b200_confidence_iou(bosip_b200_ctx* h, const double* log_fa, const double* log_fb, const double* logprior, int64_t n, int mem,
+                              double q, double* iou, double* c_a, double* c_b) {
+  API_LOCK(h);
+  return cs_confidence_iou(ctx, log_fa, log_fb, logprior, n, mem, q, iou, c_a, c_b);
 }
 
 int bosip_b200_int8_peak(bosip_b200_ctx* h, double* burst_tops, double* sustained_tops) {

@@ -79,9 +79,10 @@ struct Ctx {
   std::string err;
   cudaStream_t s_comp = nullptr, s_own = nullptr, s_in = nullptr, s_out = nullptr;  // s_comp == s_own unless set_stream
   int64_t launches = 0;
-  cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr, ev_dep = nullptr;
   int64_t user_chunk = 0;
   int var_engine = 0, var_slices = 7;  // BOSIP_B200_VAR_*: which kernel computes ||L^-1 k*||^2
+  int i8_issuers = 0;                  // MMA-issuing threads of the INT8 engine: 0 = self-check pending, else 1 or 2 (vargemm_i8.cu)
   // chunk workspace (grown on demand)
   size_t ws_bytes = 0;
   char* ws = nullptr;
@@ -209,6 +210,12 @@ int amis_log_weights(Ctx* ctx, const double* logp, const double* delta, double t
 int weighted_moments(Ctx* ctx, int d, const double* X, const double* lw, int64_t m, int mem, double* mean, double* cov, double* sums,
                      double* ws);
 int resample(Ctx* ctx, int d, const double* X, const double* ws, int64_t m, uint64_t seed, int64_t count, int mem, double* out, int64_t* idx);
+// confset.cu
+int cs_weighted_quantile(Ctx* ctx, const double* vals, const double* ws, int64_t n, int mem, double p, double* out);
+int cs_cutoff_area(Ctx* ctx, const double* vals, const double* ws, int64_t n, int mem, double c, double* out);
+int cs_set_iou(Ctx* ctx, const unsigned char* in_a, const unsigned char* in_b, const double* logprior, int64_t n, int mem, double* out);
+int cs_confidence_iou(Ctx* ctx, const double* log_fa, const double* log_fb, const double* logprior, int64_t n, int mem, double q, double* iou,
+                      double* c_a, double* c_b);
 // peaks.cu
 int fp64_peak(Ctx* ctx, double* dmma, double* dfma);
 int math_selftest(Ctx* ctx, const double* x, int64_t n, int variant, double* e_fast, double* q_fast, double* e_ref, double* q_ref);

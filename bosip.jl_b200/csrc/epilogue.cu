@@ -229,11 +229,17 @@ int launch_like_eval(Ctx* ctx, const EpiParams& ep, const double* mu, const doub
 }
 
 // ------------------------------------------------------------------------------------------------ argmax
-// Julia `argmax` semantics of BOSS's candidate maximisers: first maximal index; NaN never wins here.
+// Julia `argmax` semantics of BOSS's candidate maximisers (findmax over `isless`): first maximal index; -Inf is an ordinary
+// value (an all -Inf candidate set returns its first index); NaN orders above everything, so the first NaN wins.
 struct Best { double v; long long i; };
 __device__ __forceinline__ Best better(Best a, Best b) {
   if (b.i < 0) return a;
   if (a.i < 0) return b;
+  const bool an = a.v != a.v, bn = b.v != b.v;
+  if (an || bn) {
+    if (an && bn) return b.i < a.i ? b : a;
+    return bn ? b : a;
+  }
   if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
   return a;
 }
@@ -266,7 +272,7 @@ argmax_stage1(const double* __restrict__ vals, long long m_valid, long long offs
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < m_valid; m += (long long)gridDim.x * blockDim.x) {
     double v = vals[m];
     if (exp_vals) v = exp(v);
-    if (v == v && v > -INFINITY) { Best c; c.v = v; c.i = offset + m; b = better(b, c); }
+    Best c; c.v = v; c.i = offset + m; b = better(b, c);
   }
   b = block_best(b);
   if (threadIdx.x == 0) { sv[blockIdx.x] = b.v; si[blockIdx.x] = b.i; }

@@ -302,27 +302,45 @@ __device__ __forceinline__ Lse lse_block(Lse x, Lse* sh) {
   return x;
 }
 
+// Both TV kernels are two passes over three vectors that do not fit the 126 MB L2 at the benchmark size (2.4 GB at G = 1e8):
+// HBM-bound.  Every thread loads 4 consecutive doubles per vector with ONE 32-byte `ld.global.nc.v4.f64` (L1 bypassed: the data is
+// read once per pass) and keeps two such groups per vector in flight; a block owns a contiguous slice whose start is a multiple
+// of 1024 elements, so the vector loads are aligned whenever the base pointers are (VEC = false is the scalar path for slices
+// that start at an odd element, e.g. a rank's shard of a host vector).  Stage 2 walks its slice backwards: the tail of every
+// slice is what stage 1 left in L2.
+__device__ __forceinline__ void ld4(const double* __restrict__ p, double (&v)[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\n" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+template <bool VEC>
+__device__ __forceinline__ void tv_load4(const double* __restrict__ p, long long i0, long long hi, double fill, double (&v)[4]) {
+  if (VEC && i0 + 4 <= hi) { ld4(p + i0, v); return; }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = (i0 + e < hi) ? __ldg(p + i0 + e) : fill;
+}
+
 // out[block] = {max_a, sum_a, max_t, sum_t}: log-sum-exp pairs of lw+a and lw+t over the block's contiguous slice
+template <bool VEC>
 __global__ void __launch_bounds__(256)
-tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
+tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G, long long per,
                  double* __restrict__ out) {
   __shared__ Lse sh[8];
   __shared__ double exp_tab[EXP_TAB_N];
   load_exp_table<1>(exp_tab);
   __syncthreads();
   Lse la{-INFINITY, 0.0}, lt{-INFINITY, 0.0};
-  const long long per = (G + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
-  for (long long i0 = lo + (long long)threadIdx.x * TV_B; i0 < hi; i0 += (long long)blockDim.x * TV_B) {
+  for (long long i0 = lo + (long long)threadIdx.x * TV_B; i0 < hi; i0 += 2ll * blockDim.x * TV_B) {
+    const long long i1 = i0 + (long long)blockDim.x * TV_B;
+    double w0[4], a0[4], t0[4], w1[4], a1[4], t1[4];
+    tv_load4<VEC>(lw, i0, hi, 0.0, w0); tv_load4<VEC>(a, i0, hi, -INFINITY, a0); tv_load4<VEC>(t, i0, hi, -INFINITY, t0);
+    tv_load4<VEC>(lw, i1, hi, 0.0, w1); tv_load4<VEC>(a, i1, hi, -INFINITY, a1); tv_load4<VEC>(t, i1, hi, -INFINITY, t1);
     double va[TV_B], vt[TV_B];
 #pragma unroll
-    for (int e = 0; e < TV_B; ++e) {
-      const long long i = i0 + e;
-      const bool ok = i < hi;
-      const double w = ok ? lw[i] : 0.0;
-      va[e] = ok ? w + a[i] : -INFINITY;
-      vt[e] = ok ? w + t[i] : -INFINITY;
-    }
+    for (int e = 0; e < TV_B; ++e) { va[e] = w0[e] + a0[e]; vt[e] = w0[e] + t0[e]; }
+    lse_push_batch(la, va, exp_tab);
+    lse_push_batch(lt, vt, exp_tab);
+#pragma unroll
+    for (int e = 0; e < TV_B; ++e) { va[e] = w1[e] + a1[e]; vt[e] = w1[e] + t1[e]; }
     lse_push_batch(la, va, exp_tab);
     lse_push_batch(lt, vt, exp_tab);
   }
@@ -331,10 +349,25 @@ tv_stage1_kernel(const double* __restrict__ lw, const double* __restrict__ a, co
   if (threadIdx.x == 0) { out[4 * blockIdx.x + 0] = la.m; out[4 * blockIdx.x + 1] = la.s; out[4 * blockIdx.x + 2] = lt.m; out[4 * blockIdx.x + 3] = lt.s; }
 }
 
+// one batch of 4 grid points of stage 2: |e^(ua - nm) - e^(ut - nm)| added at the running scale nm
+__device__ __forceinline__ void tv_push_diff(Lse& ld, const double (&ua)[TV_B], const double (&ut)[TV_B], const double* exp_tab) {
+  double vm = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < TV_B; ++e) vm = fmax(vm, fmax(ua[e], ut[e]));
+  if (vm == -INFINITY) return;
+  if (vm == INFINITY) { ld.m = INFINITY; ld.s = 1.0; return; }
+  const double nm = fmax(ld.m, vm);
+  double s = (ld.m == -INFINITY) ? 0.0 : ld.s * fast_exp_neg_t<1>(nm - ld.m, exp_tab);
+#pragma unroll
+  for (int e = 0; e < TV_B; ++e) s += fabs(fast_exp_neg_t<1>(nm - ua[e], exp_tab) - fast_exp_neg_t<1>(nm - ut[e], exp_tab));
+  ld.m = nm; ld.s = s;
+}
+
 // out[block] = {m, s} with exp(m) * s = sum_i exp(lw_i) |exp(a_i - eva) - exp(t_i - evt)|  (tv.jl:64-70).  The log of the
 // reference's `log.(diffs)` is never taken: each term is formed directly at the running scale m >= lw + max(a~, t~).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
-tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G,
+tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, const double* __restrict__ t, long long G, long long per,
                  double eva_v, double evt_v, const double* __restrict__ ev_dev, double* __restrict__ out) {
   __shared__ Lse sh[8];
   __shared__ double exp_tab[EXP_TAB_N];
@@ -344,34 +377,50 @@ tv_stage2_kernel(const double* __restrict__ lw, const double* __restrict__ a, co
   const double eva = ev_dev ? ev_dev[0] : eva_v, evt = ev_dev ? ev_dev[1] : evt_v;
   const bool a_inf = isinf(eva), t_inf = isinf(evt);   // all-(-Inf) vector: its normalised density is all -Inf (tv.jl:64-66)
   Lse ld{-INFINITY, 0.0};
-  const long long per = (G + gridDim.x - 1) / gridDim.x;
   const long long lo = (long long)blockIdx.x * per, hi = min(G, lo + per);
-  for (long long i0 = lo + (long long)threadIdx.x * TV_B; i0 < hi; i0 += (long long)blockDim.x * TV_B) {
+  const long long stride = 2ll * blockDim.x * TV_B;
+  const long long n_it = (hi - lo + stride - 1) / stride;
+  for (long long it = n_it - 1; it >= 0; --it) {       // backwards: the end of the slice is what stage 1 touched last
+    const long long i0 = lo + it * stride + (long long)threadIdx.x * TV_B, i1 = i0 + (long long)blockDim.x * TV_B;
+    double w0[4], a0[4], t0[4], w1[4], a1[4], t1[4];
+    tv_load4<VEC>(lw, i0, hi, -INFINITY, w0); tv_load4<VEC>(a, i0, hi, 0.0, a0); tv_load4<VEC>(t, i0, hi, 0.0, t0);
+    tv_load4<VEC>(lw, i1, hi, -INFINITY, w1); tv_load4<VEC>(a, i1, hi, 0.0, a1); tv_load4<VEC>(t, i1, hi, 0.0, t1);
     double ua[TV_B], ut[TV_B];
-    double vm = -INFINITY;
 #pragma unroll
     for (int e = 0; e < TV_B; ++e) {
-      const long long i = i0 + e;
-      const bool ok = i < hi;
-      const double w = ok ? lw[i] : -INFINITY;
-      ua[e] = (ok && !a_inf) ? w + (a[i] - eva) : -INFINITY;   // log of the weighted normalised approx density
-      ut[e] = (ok && !t_inf) ? w + (t[i] - evt) : -INFINITY;
-      vm = fmax(vm, fmax(ua[e], ut[e]));
+      ua[e] = a_inf ? -INFINITY : w1[e] + (a1[e] - eva);   // log of the weighted normalised approx density
+      ut[e] = t_inf ? -INFINITY : w1[e] + (t1[e] - evt);
     }
-    if (vm == -INFINITY) continue;
-    if (vm == INFINITY) { ld.m = INFINITY; ld.s = 1.0; continue; }
-    const double nm = fmax(ld.m, vm);
-    double s = (ld.m == -INFINITY) ? 0.0 : ld.s * fast_exp_neg_t<1>(nm - ld.m, exp_tab);
+    tv_push_diff(ld, ua, ut, exp_tab);
 #pragma unroll
-    for (int e = 0; e < TV_B; ++e) s += fabs(fast_exp_neg_t<1>(nm - ua[e], exp_tab) - fast_exp_neg_t<1>(nm - ut[e], exp_tab));
-    ld.m = nm; ld.s = s;
+    for (int e = 0; e < TV_B; ++e) {
+      ua[e] = a_inf ? -INFINITY : w0[e] + (a0[e] - eva);
+      ut[e] = t_inf ? -INFINITY : w0[e] + (t0[e] - evt);
+    }
+    tv_push_diff(ld, ua, ut, exp_tab);
   }
   ld = lse_block(ld, sh);
   if (threadIdx.x == 0) { out[2 * blockIdx.x + 0] = ld.m; out[2 * blockIdx.x + 1] = ld.s; }
 }
 
-static int tv_blocks(Ctx* ctx, int64_t G) {
-  return (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 8 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 8);
+static int tv_blocks(Ctx* ctx, int64_t G) {   // 80 registers x 256 threads: 3 resident CTAs per SM -> two full waves at most
+  return (int)((G + 2047) / 2048 < (int64_t)ctx->sms * 6 ? (G + 2047) / 2048 : (int64_t)ctx->sms * 6);
+}
+// elements per block: a multiple of 1024 so that every thread's groups of 4 stay 32-byte aligned relative to the base pointers
+static long long tv_per(int64_t G, int nblocks) { return ((G + nblocks - 1) / nblocks + 1023) / 1024 * 1024; }
+static bool tv_aligned(const double* lw, const double* a, const double* t) {
+  return ((reinterpret_cast<uintptr_t>(lw) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(t)) & 31u) == 0;
+}
+static void tv_launch1(const double* lw, const double* a, const double* t, int64_t G, int nblocks, double* dpart, cudaStream_t st) {
+  const long long per = tv_per(G, nblocks);
+  if (tv_aligned(lw, a, t)) tv_stage1_kernel<true><<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, per, dpart);
+  else tv_stage1_kernel<false><<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, per, dpart);
+}
+static void tv_launch2(const double* lw, const double* a, const double* t, int64_t G, int nblocks, double eva, double evt, const double* ev_dev,
+                       double* dpart, cudaStream_t st) {
+  const long long per = tv_per(G, nblocks);
+  if (tv_aligned(lw, a, t)) tv_stage2_kernel<true><<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, per, eva, evt, ev_dev, dpart);
+  else tv_stage2_kernel<false><<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, per, eva, evt, ev_dev, dpart);
 }
 static size_t tv_part_bytes(int nblocks) { return ((size_t)nblocks * 4 * 8 + 3 * 8 + 255) / 256 * 256; }
 
@@ -380,8 +429,8 @@ static int tv_run(Ctx* ctx, const double* pl, const double* pa, const double* pt
                   double* dpart, int nblocks, double* out) {
   cudaStream_t st = ctx->s_comp;
   const int width = stage == 1 ? 4 : 2;
-  if (stage == 1) tv_stage1_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, dpart);
-  else tv_stage2_kernel<<<nblocks, 256, 0, st>>>(pl, pa, pt, (long long)G, eva, evt, nullptr, dpart);
+  if (stage == 1) tv_launch1(pl, pa, pt, G, nblocks, dpart, st);
+  else tv_launch2(pl, pa, pt, G, nblocks, eva, evt, nullptr, dpart, st);
   BOSIP_CUDA(ctx, cudaGetLastError());
   std::vector<double> h((size_t)nblocks * width);
   BOSIP_CUDA(ctx, cudaMemcpyAsync(h.data(), dpart, h.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -455,9 +504,9 @@ int tv_full(Ctx* ctx, const double* lw, const double* a, const double* t, int64_
   cudaStream_t st = ctx->s_comp;
   double* ev = dpart + (size_t)nblocks * 4;   // 3 doubles behind the partials (tv_part_bytes reserves them)
   const double lg = log((double)G);
-  tv_stage1_kernel<<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, dpart);
+  tv_launch1(lw, a, t, G, nblocks, dpart, st);
   tv_merge_kernel<<<1, 256, 0, st>>>(dpart, nblocks, 1, lg, ev);
-  tv_stage2_kernel<<<nblocks, 256, 0, st>>>(lw, a, t, (long long)G, 0.0, 0.0, ev, dpart);
+  tv_launch2(lw, a, t, G, nblocks, 0.0, 0.0, ev, dpart, st);
   tv_merge_kernel<<<1, 256, 0, st>>>(dpart, nblocks, 2, lg, ev);
   BOSIP_CUDA(ctx, cudaGetLastError());
   BOSIP_CUDA(ctx, cudaMemcpyAsync(tv_out, ev + 2, 8, cudaMemcpyDeviceToHost, st));

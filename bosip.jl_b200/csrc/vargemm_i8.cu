@@ -577,12 +577,57 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   return 0;
 }
 
+// bitwise comparison of the rows the GEMM wrote: part[(u * p + j) * mc + r], r < rows
+__global__ void i8_cmp_kernel(const unsigned long long* __restrict__ x, const unsigned long long* __restrict__ y, long long mc, long long rows,
+                              int nvec, unsigned int* __restrict__ mismatches) {
+  const long long total = (long long)nvec * rows;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long v = e / rows, r = e % rows;
+    if (x[v * mc + r] != y[v * mc + r]) atomicAdd(mismatches, 1u);
+  }
+}
+
+// Two issuing threads accumulate into the same TMEM columns.  Exact integer arithmetic makes the result independent of their
+// interleaving PROVIDED the tensor pipe serialises accumulates from different threads, which PTX does not promise (tcgen05.mma is
+// ordered per issuing thread only).  So the two-issuer kernel is used only after it has reproduced the single-issuer kernel bit
+// for bit on this context's first real launch (same operands, every row of the chunk); on a mismatch the context stays on one
+// issuer (~10 % slower).  BOSIP_B200_I8_ISSUERS=1 / 2 forces the choice (2: no self-check; development only).
 template <int S>
 static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
-  // two issuing threads accumulate into the same TMEM columns; exact integer arithmetic makes the result independent of their
-  // interleaving (tests/test_gpu_int8_engine.py checks the two variants bit for bit)
-  static const bool single = getenv("BOSIP_B200_I8_ISSUERS") && atoi(getenv("BOSIP_B200_I8_ISSUERS")) == 1;
-  return single ? launch_i8n<S, 1>(ctx, a, st) : launch_i8n<S, I8_ISSUERS>(ctx, a, st);
+  if (ctx->i8_issuers == 0) {
+    const char* e = getenv("BOSIP_B200_I8_ISSUERS");
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 1 || forced == 2) {
+      ctx->i8_issuers = forced;
+    } else {
+      const size_t n = (size_t)a.nsub * a.p * (size_t)a.mc;
+      double* ref = nullptr;
+      struct Tmp { double** q; ~Tmp() { if (*q) cudaFree(*q); } } tmp{&ref};
+      BOSIP_CUDA(ctx, cudaMalloc(&ref, n * 8 + 8));
+      unsigned int* d_mis = reinterpret_cast<unsigned int*>(ref + n);
+      BOSIP_CUDA(ctx, cudaMemsetAsync(d_mis, 0, 8, st));
+      I8Args b = a; b.q_part = ref;
+      BOSIP_TRY((launch_i8n<S, 1>(ctx, b, st)));
+      BOSIP_TRY((launch_i8n<S, I8_ISSUERS>(ctx, a, st)));
+      i8_cmp_kernel<<<ctx->sms * 4, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(ref), reinterpret_cast<const unsigned long long*>(a.q_part),
+                                                   a.mc, (long long)a.m_tiles * I8_BM, a.nsub * a.p, d_mis);
+      BOSIP_CUDA(ctx, cudaGetLastError());
+      unsigned int mis = 0;
+      BOSIP_CUDA(ctx, cudaMemcpyAsync(&mis, d_mis, 4, cudaMemcpyDeviceToHost, st));
+      BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+      ctx->launches += 2;
+      if (mis != 0) {   // keep the single-issuer results of this launch and stay on one issuer
+        BOSIP_CUDA(ctx, cudaMemcpyAsync(a.q_part, ref, n * 8, cudaMemcpyDeviceToDevice, st));
+        BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->i8_issuers = 1;
+        fprintf(stderr, "[bosip_b200] INT8 engine self-check: two MMA issuers differ from one in %u row sums; using one issuer\n", mis);
+      } else {
+        ctx->i8_issuers = I8_ISSUERS;
+      }
+      return 0;
+    }
+  }
+  return ctx->i8_issuers == 1 ? launch_i8n<S, 1>(ctx, a, st) : launch_i8n<S, I8_ISSUERS>(ctx, a, st);
 }
 
 // Ks8: [p][mc/128][KB][S][16 KB]; q_part: [nsub][p][mc] scratch; q: [p][mc]

@@ -58,12 +58,20 @@ def _allgather_f64(vec: np.ndarray) -> np.ndarray:
 
 
 def combine_argmax(vals: np.ndarray, idxs: np.ndarray) -> int:
-    """Index (into the gathered arrays) of the winner: largest value, lowest global index on ties; idx < 0 = no candidate."""
+    """Index (into the gathered arrays) of the winner with Julia's `argmax` semantics: largest value, lowest global index on
+    ties, -Inf an ordinary value, NaN above everything (first NaN wins); idx < 0 = that rank had no candidate."""
     best = -1
     for r in range(len(vals)):
-        if idxs[r] < 0 or np.isnan(vals[r]):
+        if idxs[r] < 0:
             continue
-        if best < 0 or vals[r] > vals[best] or (vals[r] == vals[best] and idxs[r] < idxs[best]):
+        if best < 0:
+            best = r
+            continue
+        a_nan, b_nan = np.isnan(vals[best]), np.isnan(vals[r])
+        if a_nan or b_nan:
+            if b_nan and (not a_nan or idxs[r] < idxs[best]):
+                best = r
+        elif vals[r] > vals[best] or (vals[r] == vals[best] and idxs[r] < idxs[best]):
             best = r
     return best
 
@@ -79,6 +87,55 @@ def argmax_allgather(idx: int, val: float, x: np.ndarray):
     if w < 0:
         return -1, -math.inf, x
     return int(idxs[w]), float(g[w, 0]), g[w, 3:].copy()
+
+
+def _pack_winner(idx: int, val: float, x: np.ndarray) -> np.ndarray:
+    lo, hi = (float(idx & 0xFFFFFFFF), float(idx >> 32)) if idx >= 0 else (-1.0, -1.0)
+    return np.concatenate([[val, lo, hi], np.asarray(x, dtype=np.float64)])
+
+
+def _unpack_winners(g: np.ndarray):
+    idxs = np.array([(-1 if row[1] < 0 else (int(row[2]) << 32) | int(row[1])) for row in g], dtype=np.int64)
+    w = combine_argmax(g[:, 0], idxs)
+    if w < 0:
+        return -1, -math.inf, g[0, 3:].copy()
+    return int(idxs[w]), float(g[w, 0]), g[w, 3:].copy()
+
+
+class DeviceArgmaxGather:
+    """Device-resident argmax exchange: each step's per-rank winner (value, global index, x) is uploaded from a pinned staging
+    slot and all-gathered on the device with NO host synchronisation; `result()` reads the last gathered table once (after the
+    caller's own synchronise) and reduces it with `combine_argmax`.  Single process: keeps the local winner."""
+
+    def __init__(self, d: int, slots: int = 64):
+        import torch
+        self.dist = _dist()
+        self.d, self.slots, self.k = d, slots, 0
+        self.local = None
+        if self.dist is not None:
+            self.world = self.dist.get_world_size()
+            dev = _device()
+            pin = dev.type == "cuda"
+            self.stage = torch.empty((slots, 3 + d), dtype=torch.float64, pin_memory=pin)
+            self.send = torch.empty(3 + d, dtype=torch.float64, device=dev)
+            self.table = torch.empty((self.world, 3 + d), dtype=torch.float64, device=dev)
+
+    def push(self, idx: int, val: float, x=None):
+        x = np.zeros(self.d) if x is None else x
+        if self.dist is None:
+            self.local = (int(idx), float(val), np.asarray(x, dtype=np.float64))
+            return
+        import torch
+        slot = self.stage[self.k % self.slots]
+        slot.copy_(torch.from_numpy(_pack_winner(idx, val, x)))
+        self.k += 1
+        self.send.copy_(slot, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.table.view(-1), self.send)
+
+    def result(self):
+        if self.dist is None:
+            return self.local if self.local is not None else (-1, -math.inf, np.zeros(self.d))
+        return _unpack_winners(self.table.cpu().numpy())
 
 
 def allreduce_sum(v: np.ndarray) -> np.ndarray:

@@ -10,8 +10,9 @@
       /root/reference/src/metrics/opt_mmd.jl:17-54
 
 What runs on the GPU: the proposal draws, log_pi(xs) (the fused posterior sweep), the proposal-mixture pdf sums, the log-weights,
-exp_weights + weighted mean/covariance, the multinomial down-sampling and calc_mmd.  What stays on the host: the d x d Cholesky
-of a proposal covariance, the sort-based weighted quantile of <= 1e5 closure values, and the length-scale optimiser of OptMMD."""
+exp_weights + weighted mean/covariance, the multinomial down-sampling, calc_mmd, and the confidence-set reductions (weighted
+quantile by a device sort + scan, cut-off area, IoU).  What stays on the host: the d x d Cholesky of a proposal covariance and
+the length-scale optimiser of OptMMD."""
 from __future__ import annotations
 
 import ctypes as C
@@ -61,6 +62,8 @@ class NormalProposal:
         else:
             out = np.empty((d, count), order="F"); ptr, mem = out.ctypes.data, L.HOST
         Lf = np.asfortranarray(self.Lc)
+        if device:
+            ctx.order_after_torch()
         ctx._check(ctx.lib.bosip_b200_mvnormal_sample(ctx.h, d, _dptr(self.mu), _dptr(Lf), int(seed), int(offset), int(count), mem, ptr))
         return out
 
@@ -87,6 +90,8 @@ def mixture_pdf_sum(qs, X, delta=None, ctx: Optional[Context] = None):
     mus = np.asfortranarray(np.stack([q.mu for q in qs], axis=1))
     Linvs = np.ascontiguousarray(np.stack([np.asfortranarray(q.Linv).T for q in qs]))   # each block: column-major d x d
     ln = np.ascontiguousarray([q.lognorm for q in qs], dtype=np.float64)
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
     ctx._check(ctx.lib.bosip_b200_mixture_pdf_sum(ctx.h, d, len(qs), _dptr(mus), _dptr(Linvs), _dptr(ln), px, M, mem, 1 if acc else 0, pd))
     return delta
 
@@ -101,6 +106,8 @@ def amis_log_weights(log_p, delta, t: float, out=None, ctx: Optional[Context] = 
         out, po = _out((M,), mem, like=kp if mem == L.DEVICE else None)
     else:
         ko, po, _, _ = _colmajor(out)
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
     ctx._check(ctx.lib.bosip_b200_amis_log_weights(ctx.h, pp, pd, float(t), M, mem, po))
     return out
 
@@ -117,6 +124,8 @@ def weighted_moments(X, log_ws, want_ws: bool = False, ctx: Optional[Context] = 
     ws, pws = (None, None)
     if want_ws:
         ws, pws = _out((M,), mem, like=kx if mem == L.DEVICE else None)
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
     try:
         ctx._check(ctx.lib.bosip_b200_weighted_moments(ctx.h, d, px, pw, M, mem, _dptr(mean), _dptr(cov), _dptr(sums), pws))
     except BosipB200Error as e:
@@ -247,6 +256,8 @@ def resample(xs, ws, count: int, seed: int = 0, ctx: Optional[Context] = None, r
             idx = torch.empty(count, dtype=torch.int64, device=kx.device); pi = idx.data_ptr()
         else:
             idx = np.empty(count, dtype=np.int64); pi = idx.ctypes.data
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
     ctx._check(ctx.lib.bosip_b200_resample(ctx.h, d, px, pw, M, int(seed), int(count), mem, po, pi))
     return (out, idx) if return_index else out
 
@@ -259,57 +270,86 @@ def sample_posterior_pure(sampler: AMISSampler, logpost: Callable, bounds, count
 
 
 # ----------------------------------------------------------------------------------------------- confidence sets
-def weighted_quantile(vals, ws, p: float) -> float:
-    """quantile(vals, Distributions.weights(ws), p) as StatsBase.jl defines it for non-frequency weights: zero weights dropped,
-    values sorted, h = p (W - w_1) + w_1 on the cumulative weights, linear interpolation between the neighbouring values."""
-    v = np.asarray(vals, dtype=np.float64); w = np.asarray(ws, dtype=np.float64)
-    if v.size == 0:
+def _vec(x):
+    """(keepalive, address, mem, n) of a length-n float64 vector (NumPy or torch)."""
+    return _colmajor(x if _is_torch(x) else np.asarray(x, dtype=np.float64).reshape(-1))
+
+
+def weighted_quantile(vals, ws, p: float, ctx: Optional[Context] = None) -> float:
+    """quantile(vals, Distributions.weights(ws), p) as StatsBase.jl defines it for non-frequency weights (zero weights dropped,
+    values sorted, h = p (W - w_1) + w_1 on the cumulative weights, linear interpolation) -- on the device: bitonic sort of
+    (value, index) pairs, fixed-order prefix sum of the weights, one interpolation (csrc/confset.cu).  ws=None: unit weights."""
+    ctx = ctx or default_context()
+    kv, pv, mem, n = _vec(vals)
+    if n == 0:
         raise ValueError("quantile of an empty array is undefined")
-    if np.any(np.isnan(v)):
-        return float("nan")
-    keep = w != 0
-    order = np.argsort(v[keep], kind="stable")
-    vs, wsrt = v[keep][order], w[keep][order]
-    wsum = float(np.sum(w))
-    h = p * (wsum - wsrt[0]) + wsrt[0]
-    S = np.cumsum(wsrt)
-    k = int(np.searchsorted(S, h, side="right"))       # first k with S_k > h  (the reference loops `while Sk <= h`)
-    if k >= len(vs):
-        return float(vs[-1])
-    Sk, Skold = S[k], (S[k - 1] if k > 0 else 0.0)
-    vk, vkold = vs[k], (vs[k - 1] if k > 0 else 0.0)
-    return float(vkold + (h - Skold) / (Sk - Skold) * (vk - vkold))
+    kw = pw = None
+    if ws is not None:
+        kw, pw, m2, n2 = _vec(ws)
+        if m2 != mem or n2 != n:
+            raise ValueError("vals and ws must have the same length and live in the same memory space")
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
+    out = C.c_double()
+    ctx._check(ctx.lib.bosip_b200_weighted_quantile(ctx.h, pv, pw, n, mem, float(p), C.byref(out)))
+    return out.value
 
 
-def find_cutoff(target_pdf, xs, ws_or_q, q: Optional[float] = None) -> float:
+def find_cutoff(target_pdf, xs, ws_or_q, q: Optional[float] = None, ctx: Optional[Context] = None) -> float:
     """find_cutoff(target_pdf, xs, q) / find_cutoff(target_pdf, xs, ws, q) -- confidence_set.jl:19-27; target_pdf is called once
     on the whole sample matrix (the batched closure) instead of column by column."""
-    vals = np.asarray(_host(target_pdf(xs)), dtype=np.float64)
+    vals = target_pdf(xs)
     if q is None:
-        ws, q = np.ones(vals.size), float(ws_or_q)
-    else:
-        ws = np.asarray(_host(ws_or_q), dtype=np.float64)
-    return weighted_quantile(vals, ws, 1.0 - q)
+        return weighted_quantile(vals, None, 1.0 - float(ws_or_q), ctx)
+    return weighted_quantile(vals, ws_or_q, 1.0 - q, ctx)
 
 
-def approx_cutoff_area(target_pdf, xs, ws_or_c, c: Optional[float] = None) -> float:
+def approx_cutoff_area(target_pdf, xs, ws_or_c, c: Optional[float] = None, ctx: Optional[Context] = None) -> float:
     """approx_cutoff_area(target_pdf, xs, c) / (target_pdf, xs, ws, c) -- confidence_set.jl:47-56"""
-    vals = np.asarray(_host(target_pdf(xs)), dtype=np.float64)
+    ctx = ctx or default_context()
+    kv, pv, mem, n = _vec(target_pdf(xs))
+    kw = pw = None
     if c is None:
-        ws, c = np.ones(vals.size), float(ws_or_c)
+        c = float(ws_or_c)
     else:
-        ws = np.asarray(_host(ws_or_c), dtype=np.float64)
-    with np.errstate(divide="ignore"):
-        wn = np.exp(np.log(ws) - np.log(np.sum(ws)))
-    return float(np.sum(wn[vals >= c]))
+        kw, pw, m2, _ = _vec(ws_or_c)
+        if m2 != mem:
+            raise ValueError("values and weights must live in the same memory space")
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
+    out = C.c_double()
+    ctx._check(ctx.lib.bosip_b200_cutoff_area(ctx.h, pv, pw, n, mem, float(c), C.byref(out)))
+    return out.value
 
 
-def set_iou(in_A, in_B, prior_logpdf_vals) -> float:
+def set_iou(in_A, in_B, prior_logpdf_vals, ctx: Optional[Context] = None) -> float:
     """set_iou(in_A, in_B, x_prior, xs) -- confidence_set.jl:73-81 with logpdf(x_prior, xs) passed in (ws = 1 / pdf, normalised)."""
-    ws = np.exp(-np.asarray(prior_logpdf_vals, dtype=np.float64))
-    ws = ws / np.sum(ws)
-    a, b = np.asarray(in_A, bool), np.asarray(in_B, bool)
-    return float(np.sum(ws[a & b]) / np.sum(ws[a | b]))
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(_host(in_A), dtype=np.uint8); b = np.ascontiguousarray(_host(in_B), dtype=np.uint8)
+    lp = np.ascontiguousarray(_host(prior_logpdf_vals), dtype=np.float64)
+    if not (a.size == b.size == lp.size):
+        raise ValueError("in_A, in_B and the prior log-pdf values must have the same length")
+    out = C.c_double()
+    ctx._check(ctx.lib.bosip_b200_set_iou(ctx.h, a.ctypes.data, b.ctypes.data, lp.ctypes.data, a.size, L.HOST, C.byref(out)))
+    return out.value
+
+
+def confidence_iou(log_f_approx, log_f_expect, prior_logpdf_vals, q: float, ctx: Optional[Context] = None):
+    """The core of calculate(::AEConfidence, bosip) (ae_confidence.jl:66-78) on the two closures' log-values: returns
+    (iou, c_approx, c_expect).  One device call: two weighted quantiles + the IoU reduction."""
+    ctx = ctx or default_context()
+    ka, pa, mem, n = _vec(log_f_approx); kb, pb, m2, _ = _vec(log_f_expect)
+    if _is_torch(ka) and not _is_torch(prior_logpdf_vals):
+        import torch
+        prior_logpdf_vals = torch.as_tensor(np.asarray(prior_logpdf_vals, dtype=np.float64), device=ka.device)
+    kl, pl, m3, _ = _vec(prior_logpdf_vals)
+    if not (mem == m2 == m3):
+        raise ValueError("inputs must live in the same memory space")
+    if mem == L.DEVICE:
+        ctx.order_after_torch()
+    iou, ca, cb = C.c_double(), C.c_double(), C.c_double()
+    ctx._check(ctx.lib.bosip_b200_confidence_iou(ctx.h, pa, pb, pl, n, mem, float(q), C.byref(iou), C.byref(ca), C.byref(cb)))
+    return iou.value, ca.value, cb.value
 
 
 def _host(v):
@@ -319,7 +359,7 @@ def _host(v):
 @dataclass
 class AEConfidence:
     """AEConfidence(; max_iters, samples, xs, q, r) -- term_conds/ae_confidence.jl:19-47.  calculate() evaluates both closures on the
-    whole sample matrix in one fused device sweep each (the reference calls them column by column, :68-77)."""
+    whole sample matrix in ONE fused device sweep (the reference calls them column by column, :68-77) and reduces them on the device."""
     max_iters: Optional[int] = None
     samples: int = 10_000
     xs: Optional[np.ndarray] = None
@@ -329,15 +369,13 @@ class AEConfidence:
 
     def calculate(self, bosip) -> float:
         """calculate(cond, bosip) -- ae_confidence.jl:59-79: IoU of the q-confidence regions of the approximate and the expected posterior."""
+        from .api import posterior_eval
         xs = self.xs if self.xs is not None else bosip.x_prior.rand(self.samples, np.random.default_rng(self.seed))
-        f_approx = approx_posterior(bosip, normalize=False)
-        f_expect = posterior_mean(bosip, normalize=False)
-        va = np.asarray(f_approx(xs), dtype=np.float64); ve = np.asarray(f_expect(xs), dtype=np.float64)
-        xs_logpdf = bosip.x_prior.logpdf(xs)
-        with np.errstate(divide="ignore"):
-            ws_a = np.exp(np.log(va) - xs_logpdf); ws_e = np.exp(np.log(ve) - xs_logpdf)
-        c_a = weighted_quantile(va, ws_a, 1.0 - self.q); c_e = weighted_quantile(ve, ws_e, 1.0 - self.q)
-        return set_iou(va > c_a, ve > c_e, xs_logpdf)
+        post = bosip.model_posterior()
+        res = posterior_eval(post, bosip.likelihood, bosip.x_prior, xs, L.WANT_APPROX | L.WANT_MEAN)
+        xs_logpdf = bosip.x_prior.logpdf(_host(xs))
+        ctx = (post[0] if isinstance(post, (list, tuple)) else post).ctx
+        return confidence_iou(res["log_approx_post"], res["log_post_mean"], xs_logpdf, self.q, ctx)[0]
 
     def __call__(self, bosip) -> bool:
         """True = keep going (the IoU has not reached r yet), like every BosipTermCond (ae_confidence.jl:49-57)."""

@@ -128,6 +128,11 @@ const char* bosip_b200_last_error(const bosip_b200_ctx* ctx);
  * current stream) so that the caller's events bracket them; NULL restores the context's own stream.  The H2D/D2H
  * staging streams stay internal.  Every entry point still returns only when its outputs are complete. */
 int bosip_b200_set_stream(bosip_b200_ctx* ctx, void* cuda_stream);
+/* Order the context's compute stream after everything already enqueued on `producer_stream` (a `cudaStream_t` passed as
+ * void*; NULL = the legacy default stream).  Callers that hand over DEVICE buffers written (or freed and recycled) by work on
+ * another stream call this first: the context's own streams are non-blocking, so nothing orders them implicitly.  HOST buffers
+ * need no ordering. */
+int bosip_b200_stream_wait(bosip_b200_ctx* ctx, void* producer_stream);
 /* Number of kernels this context has launched since creation (bench.py: gpu_launches). */
 int bosip_b200_launch_count(bosip_b200_ctx* ctx, int64_t* out);
 /* Upper bound for the number of query points processed per internal chunk (0 = library default). */
@@ -144,6 +149,11 @@ int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
 #define BOSIP_B200_VAR_INT8 1
 #define BOSIP_B200_VAR_AUTO 2 /* default: INT8 for N >= 128 training points, FP64 below */
 int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
+/* How many threads issue tcgen05.mma in the INT8 engine of this context: 2 (default) only after a one-off self-check has
+ * shown, on the first real chunk, that the two-issuer kernel reproduces the single-issuer kernel bit for bit (PTX orders
+ * tcgen05.mma per issuing thread only); 1 after a mismatch or with BOSIP_B200_I8_ISSUERS=1; 0 = not decided yet (no INT8 launch
+ * so far). */
+int bosip_b200_i8_issuers(bosip_b200_ctx* ctx, int* out);
 /* ---- AMIS importance sampler, inner loop (src/samplers/amis/amis_method.jl:26-83,126-134;
  *      src/samplers/amis/proposal_distributions/normal.jl:75-100; src/sampling.jl:55-57).  The samples, log_P, Delta and
  *      log_Omega can stay in HBM between iterations (mem = BOSIP_B200_DEVICE); log_pi(xs) is bosip_b200_posterior_eval. ---- */
@@ -191,6 +201,8 @@ int bosip_b200_gp_load_factors(bosip_b200_ctx* ctx, int kernel_id, int d, int N,
 /* Download what the device holds (any pointer may be NULL): L (p x N x N col-major), Linv (same layout),
  * a (N x p).  For tests and for ncclBroadcast-free host replication. */
 int bosip_b200_gp_get_factors(bosip_b200_gp* gp, double* L, double* Linv, double* a);
+/* Shape of a conditioned GP (any pointer may be NULL): input dimension d, training points N, output dimension p. */
+int bosip_b200_gp_dims(const bosip_b200_gp* gp, int* d, int* N, int* p);
 int bosip_b200_gp_free(bosip_b200_gp* gp);
 
 /* ---- BOSS.mean / var / mean_and_var (model_post, X::AbstractMatrix)  -> p x M
@@ -211,7 +223,8 @@ int bosip_b200_posterior_eval(bosip_b200_gp* gp, const bosip_b200_like_normal* l
 
 /* Same sweep, plus the acquisition argmax over the evaluated points in the same pass (acq = BOSIP_B200_ACQ_* or -1 for
  * none): what a SamplingAM-style maximiser needs when the per-point values are wanted too.  best_idx is
- * index_offset + (0-based position in Xq), -1 if no finite value; ties -> lowest index. */
+ * index_offset + (0-based position in Xq) with Julia's `argmax` semantics: first maximal index, -Inf is an ordinary value
+ * (an all -Inf set returns its first index), a NaN value wins over everything (first NaN); -1 only when M == 0. */
 int bosip_b200_posterior_eval_argmax(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
                                      const double* Xq, int64_t M, int mem, const double* mean_at_Xq, unsigned want,
                                      double* log_approx_post, double* log_post_mean, double* log_post_var,
@@ -242,12 +255,18 @@ int bosip_b200_normal_likelihood_eval(bosip_b200_ctx* ctx, const bosip_b200_like
 /* ---- acquisition over a candidate set + argmax: MaxVar / LogMaxVar closure (src/acquisitions/maxvar.jl:9-11,
  *      logmaxvar.jl:13-15) evaluated by BOSS's SamplingAM / GridAM (docs/src/hyperparams.md:69). ----------- */
 /* Candidates index_offset .. index_offset+M-1 of the source (so that ranks can shard one global set).
- * Ties resolve to the lowest global index (Julia `argmax`); NaN values are never selected.
- * best_idx is the GLOBAL 0-based index, best_x the d coordinates of the winner; if every value is -Inf/NaN
- * best_idx = -1. */
+ * Julia `argmax` semantics: ties resolve to the lowest global index, -Inf is an ordinary value, NaN wins (first NaN).
+ * best_idx is the GLOBAL 0-based index, best_x the d coordinates of the winner; best_idx = -1 only when M == 0. */
 int bosip_b200_acq_argmax(bosip_b200_gp* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
                           const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq,
                           int64_t* best_idx, double* best_val, double* best_x);
+/* MultiFittedParams variants (src/posterior/log_posterior.jl:86-95,120-129,153-162 under src/acquisitions/maxvar.jl:9-11 and
+ * src/posterior/evidence.jl:19-24): the same sweeps over an ensemble of n_samples conditioned GPs, averaged in linear space. */
+int bosip_b200_acq_argmax_bi(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like,
+                             const bosip_b200_prior* prior, const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq,
+                             int64_t* best_idx, double* best_val, double* best_x);
+int bosip_b200_evidence_sum_bi(bosip_b200_gp* const* gps, int n_samples, const bosip_b200_like_normal* like,
+                               const bosip_b200_prior* prior, const double* xs, int64_t S, int mem, unsigned which, double* sum_out);
 /* ---- marginal-integration sweep: `_compute_marginals_int` (ext/CairoExt.jl:146-246), the heaviest batched caller of the
  *      path.  lhc is the d x G Latin-hypercube sample matrix (host).  For every dimension k and grid value i (diagonal), and for
  *      every pair a < b and grid values (ia, ib), row k (rows a, b) of lhc is overwritten with range(lb, ub; length = grid_size)
@@ -288,6 +307,64 @@ int bosip_b200_tv_stage2(bosip_b200_ctx* ctx, const double* log_ws, const double
                          int mem, double ev_approx, double ev_true, double* out2);
 int bosip_b200_tv(bosip_b200_ctx* ctx, const double* log_ws, const double* a, const double* t, int64_t G, int mem,
                   double* tv_out);
+
+/* ---- confidence sets (src/utils/confidence_set.jl:19-81) and the AEConfidence termination condition's core
+ *      (src/term_conds/ae_confidence.jl:59-79).  All vectors have n entries in memory space `mem`; scalars come back on the host. */
+/* quantile(vals, Distributions.weights(ws), p) as StatsBase defines it for non-frequency weights (zero weights dropped, values
+ * sorted, h = p (W - w_1) + w_1, linear interpolation on the cumulative weights): what find_cutoff calls with p = 1 - q
+ * (confidence_set.jl:24-26).  ws == NULL: unit weights.  Any NaN value -> NaN. */
+int bosip_b200_weighted_quantile(bosip_b200_ctx* ctx, const double* vals, const double* ws, int64_t n, int mem, double p, double* out);
+/* approx_cutoff_area (confidence_set.jl:52-56): sum of exp(log ws - log sum ws) over the entries with vals >= c. */
+int bosip_b200_cutoff_area(bosip_b200_ctx* ctx, const double* vals, const double* ws, int64_t n, int mem, double c, double* out);
+/* set_iou (confidence_set.jl:73-81): in_A, in_B are n bytes (Julia Vector{Bool}), logprior = logpdf.(x_prior, eachcol(xs));
+ * ws = 1 ./ pdf, normalised; out = sum ws[A & B] / sum ws[A | B]. */
+int bosip_b200_set_iou(bosip_b200_ctx* ctx, const uint8_t* in_A, const uint8_t* in_B, const double* logprior, int64_t n, int mem, double* out);
+/* calculate(::AEConfidence, bosip) from the two closures' LOG values on the samples xs (log_f_approx = log_approx_posterior(xs),
+ * log_f_expect = log_posterior_mean(xs), e.g. straight from bosip_b200_posterior_eval with mem = DEVICE): f = exp(log f),
+ * ws = exp(log f - logprior), c = quantile(f, weights(ws), 1 - q) for each closure, IoU of {f_approx > c_approx} and
+ * {f_expect > c_expect} under ws = 1 / pdf(prior).  c_approx / c_expect (optional) return the two cut-offs. */
+int bosip_b200_confidence_iou(bosip_b200_ctx* ctx, const double* log_f_approx, const double* log_f_expect, const double* logprior,
+                              int64_t n, int mem, double q, double* iou, double* c_approx, double* c_expect);
+
+/* ---- multi-GPU from ONE host process: what a Julia host calling through BOSS.maximize_acquisition
+ *      (src/main.jl:98-101, docs/src/hyperparams.md:69) or the posterior closures gets without torchrun.  bosip_b200_init_multi
+ *      opens one context per device (devs == NULL: devices 0..ndev-1); the fit is replicated on every device; every `_multi`
+ *      call shards its points into contiguous ranges (first M % ndev devices get one extra point, global indices preserved),
+ *      runs the shards concurrently on one host thread per device and combines the few doubles that come back in fixed rank
+ *      order.  Large buffers are HOST memory (a device pointer belongs to one GPU).  Per-point outputs and the argmax are
+ *      bit-identical to the one-GPU entry points; sums differ only in the association of the per-device partials. ---------- */
+typedef struct bosip_b200_multi bosip_b200_multi;       /* N contexts, one per device */
+typedef struct bosip_b200_gp_multi bosip_b200_gp_multi; /* N replicas of one conditioned GP */
+int bosip_b200_init_multi(int ndev, const int* devs, bosip_b200_multi** out);
+int bosip_b200_shutdown_multi(bosip_b200_multi* mh);
+int bosip_b200_multi_size(const bosip_b200_multi* mh);
+/* Borrow the per-device context / GP replica (e.g. to select the variance engine or read timings); owned by the multi handle. */
+bosip_b200_ctx* bosip_b200_multi_context(bosip_b200_multi* mh, int rank);
+bosip_b200_gp* bosip_b200_gp_multi_replica(bosip_b200_gp_multi* gp, int rank);
+/* Message of the last failed `_multi` call (mh == NULL: of the last failed bosip_b200_init_multi on this thread). */
+const char* bosip_b200_multi_last_error(const bosip_b200_multi* mh);
+/* bosip_b200_gp_fit on every device (src/posterior/log_posterior.jl:81). */
+int bosip_b200_gp_fit_multi(bosip_b200_multi* mh, int kernel_id, int d, int N, int p, const double* X, const double* Y,
+                            const double* lambda, const double* alpha, const double* sigma, const double* mean_at_X,
+                            const bosip_b200_gp_opts* opts, bosip_b200_gp_multi** out);
+int bosip_b200_gp_free_multi(bosip_b200_gp_multi* gp);
+/* bosip_b200_posterior_eval_argmax over contiguous M ranges (src/posterior/log_posterior.jl:15-61); acq = -1: no argmax. */
+int bosip_b200_posterior_eval_multi(bosip_b200_gp_multi* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                                    const double* Xq, int64_t M, const double* mean_at_Xq, unsigned want, double* log_approx_post,
+                                    double* log_post_mean, double* log_post_var, int64_t* n_clamped, int acq, int64_t index_offset,
+                                    int64_t* best_idx, double* best_val);
+/* bosip_b200_acq_argmax over contiguous candidate ranges (src/acquisitions/maxvar.jl:9-11, logmaxvar.jl:13-15). */
+int bosip_b200_acq_argmax_multi(bosip_b200_gp_multi* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                                const bosip_b200_cand_src* src, int64_t M, int64_t index_offset, int acq, int64_t* best_idx,
+                                double* best_val, double* best_x);
+/* bosip_b200_evidence_sum over contiguous sample ranges (src/posterior/evidence.jl:19-24). */
+int bosip_b200_evidence_sum_multi(bosip_b200_gp_multi* gp, const bosip_b200_like_normal* like, const bosip_b200_prior* prior,
+                                  const double* xs, int64_t S, unsigned which, double* sum_out);
+/* calc_mmd with the tile grid dealt round-robin to the devices (src/metrics/mmd.jl:23-28); A, B host. */
+int bosip_b200_mmd_multi(bosip_b200_multi* mh, int kernel_id, int d, const double* lambda, const double* A, int64_t n,
+                         const double* B, int64_t m, double* mmd2_out);
+/* calc_tv with the grid cut into contiguous slices, (max, sum) pairs merged between the stages (src/metrics/tv.jl:59-73). */
+int bosip_b200_tv_multi(bosip_b200_multi* mh, const double* log_ws, const double* a, const double* t, int64_t G, double* tv_out);
 
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------------- */
 /* FP64 pipe microbenchmark on this GPU: DMMA (mma.sync m8n8k4.f64) and DFMA TFLOP/s -- the roofline

@@ -228,9 +228,16 @@ def test_argmax_matches_oracle_ties_and_sources(bb, ctx):
     Xt = np.concatenate([Xq[:, :100], Xq[:, [oi]], Xq[:, 100:200], Xq[:, [oi]]], axis=1)
     bi, _, _ = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(Xt))
     assert bi == 100
-    # every candidate outside the prior support -> no winner
+    # every candidate outside the prior support: all values are -Inf and Julia's argmax returns the FIRST index (labelled by
+    # index_offset); an empty candidate set is the only case without a winner
     far = np.full((2, 300), 9.0)
-    bi, bv, _ = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(far))
+    bi, bv, bx = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(far))
+    assert bi == 0 and bv == -np.inf and np.array_equal(bx, far[:, 0])
+    bi, bv, _ = bb.acq_argmax(post, like, prior, bb.MaxVar(), bb.CandidateSource.from_points(far), 100, 200)
+    assert bi == 100 and bv == 0.0                                           # MaxVar = exp(log V) = 0 everywhere
+    mixed = np.concatenate([far[:, :5], Xq[:, :50]], axis=1)
+    assert bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(mixed))[0] >= 5
+    bi, bv, _ = bb.acq_argmax(post, like, prior, bb.LogMaxVar(), bb.CandidateSource.from_points(far[:, :0]))
     assert bi == -1 and bv == -np.inf
     # device-generated candidates == host Philox mirror == explicit points, and sharded ranges compose
     src = bb.CandidateSource.philox(20261019, pr.lb, pr.ub, 50000)

@@ -144,21 +144,63 @@ def test_resample_and_sample_posterior_pure(bb, ctx):
     assert abs(m) < 1e-12
 
 
+def test_confidence_set_device_kernels_edge_cases(bb, ctx):
+    """csrc/confset.cu against the oracle's loop-for-loop restatement of src/utils/confidence_set.jl:19-81 (+ StatsBase's weighted
+    quantile): tiny and ragged sizes around the 2048-element sort tile, ties, zero weights, NaN, device-resident inputs."""
+    import torch
+    rng = np.random.default_rng(12)
+    for n in (1, 2, 3, 17, 400, 2047, 2048, 2049, 5000, 70001):
+        v = rng.normal(size=n); w = rng.uniform(0.0, 2.0, n); w[rng.random(n) < 0.2] = 0.0
+        if not np.any(w):
+            w[0] = 1.0
+        for p in (0.0, 0.03, 0.5, 0.8, 1.0):
+            assert bb.weighted_quantile(v, w, p, ctx) == pytest.approx(orc.weighted_quantile(v, w, p), rel=1e-12, abs=1e-15)
+        v[n // 2] = v[0]                                              # ties
+        assert bb.weighted_quantile(v, w, 0.37, ctx) == pytest.approx(orc.weighted_quantile(v, w, 0.37), rel=1e-12, abs=1e-15)
+        vd, wd = torch.as_tensor(v, device="cuda"), torch.as_tensor(w, device="cuda")
+        assert bb.weighted_quantile(vd, wd, 0.37, ctx) == bb.weighted_quantile(v, w, 0.37, ctx)      # host and device buffers: same bits
+        assert bb.weighted_quantile(v, None, 0.25, ctx) == pytest.approx(orc.weighted_quantile(v, np.ones(n), 0.25), rel=1e-12, abs=1e-15)
+    xs = rng.normal(size=(2, 500)); pdf = lambda X: np.exp(-0.5 * (np.asarray(X) ** 2).sum(0)); ws = rng.uniform(0.5, 1.5, 500)   # noqa: E731
+    vals = pdf(xs)
+    for q in (0.5, 0.8, 0.95):
+        c = bb.find_cutoff(pdf, xs, ws, q, ctx)
+        assert c == pytest.approx(orc.find_cutoff(vals, ws, q), rel=1e-12)
+        assert bb.find_cutoff(pdf, xs, q, ctx=ctx) == pytest.approx(orc.find_cutoff(vals, np.ones(500), q), rel=1e-12)
+        assert bb.approx_cutoff_area(pdf, xs, ws, c, ctx) == pytest.approx(orc.approx_cutoff_area(vals, ws, c), rel=1e-12)
+        assert bb.approx_cutoff_area(pdf, xs, ws, c, ctx) == pytest.approx(q, abs=0.02)        # the cut-off encloses ~q of the weight
+        assert bb.approx_cutoff_area(pdf, xs, c, ctx=ctx) == pytest.approx(orc.approx_cutoff_area(vals, np.ones(500), c), rel=1e-12)
+    in_a = vals >= np.quantile(vals, 0.3); in_b = pdf(xs - 0.4) >= np.quantile(pdf(xs - 0.4), 0.3)
+    lp = -0.5 * (xs ** 2).sum(0) / 9.0
+    assert bb.set_iou(in_a, in_b, lp, ctx) == pytest.approx(orc.set_iou(in_a, in_b, np.exp(lp)), rel=1e-12)
+    assert bb.set_iou(in_a, in_a, lp, ctx) == pytest.approx(1.0, rel=1e-14)
+    assert np.isnan(bb.weighted_quantile(np.array([1.0, np.nan]), np.ones(2), 0.5, ctx))
+    # the fused AEConfidence core on log-values: host buffers == device buffers == the oracle's three steps
+    n = 30011
+    la = rng.normal(-3.0, 2.0, n); lb = la + rng.normal(0.0, 0.3, n); lpr = rng.normal(-2.0, 0.5, n)
+    iou, ca, cb = bb.confidence_iou(la, lb, lpr, 0.9, ctx)
+    va, vb = np.exp(la), np.exp(lb)
+    oca = orc.find_cutoff(va, np.exp(np.log(va) - lpr), 0.9); ocb = orc.find_cutoff(vb, np.exp(np.log(vb) - lpr), 0.9)
+    assert ca == pytest.approx(oca, rel=1e-12) and cb == pytest.approx(ocb, rel=1e-12)
+    assert iou == pytest.approx(orc.set_iou(va > oca, vb > ocb, np.exp(lpr)), rel=1e-10)
+    dev = bb.confidence_iou(torch.as_tensor(la, device="cuda"), torch.as_tensor(lb, device="cuda"), lpr, 0.9, ctx)
+    assert dev == (iou, ca, cb)
+
+
 def test_confidence_sets_and_ae_confidence_vs_oracle(bb, ctx):
     rng = np.random.default_rng(4)
     vals = rng.gamma(2.0, 1.0, 5000); ws = rng.gamma(1.0, 1.0, 5000); ws[::11] = 0.0
     for p in (0.0, 0.05, 0.5, 0.95, 1.0):
-        assert bb.weighted_quantile(vals, ws, p) == pytest.approx(orc.weighted_quantile(vals, ws, p), rel=1e-13)
-    assert bb.weighted_quantile([1, 2, 3, 4], np.ones(4), 0.5) == 2.5     # StatsBase: h = p (W - w1) + w1 on the cumulative weights
+        assert bb.weighted_quantile(vals, ws, p, ctx) == pytest.approx(orc.weighted_quantile(vals, ws, p), rel=1e-12)
+    assert bb.weighted_quantile([1, 2, 3, 4], np.ones(4), 0.5, ctx) == 2.5     # StatsBase: h = p (W - w1) + w1 on the cumulative weights
     xs = rng.uniform(-1, 1, (2, 5000))
     f = lambda X: np.exp(-np.sum(np.asarray(X) ** 2, axis=0))             # noqa: E731
-    c = bb.find_cutoff(f, xs, ws, 0.8)
-    assert c == pytest.approx(orc.find_cutoff(f(xs), ws, 0.8), rel=1e-13)
-    assert bb.find_cutoff(f, xs, 0.8) == pytest.approx(orc.find_cutoff(f(xs), np.ones(5000), 0.8), rel=1e-13)
-    assert bb.approx_cutoff_area(f, xs, ws, c) == pytest.approx(orc.approx_cutoff_area(f(xs), ws, c), rel=1e-12)
+    c = bb.find_cutoff(f, xs, ws, 0.8, ctx)
+    assert c == pytest.approx(orc.find_cutoff(f(xs), ws, 0.8), rel=1e-12)
+    assert bb.find_cutoff(f, xs, 0.8, ctx=ctx) == pytest.approx(orc.find_cutoff(f(xs), np.ones(5000), 0.8), rel=1e-12)
+    assert bb.approx_cutoff_area(f, xs, ws, c, ctx) == pytest.approx(orc.approx_cutoff_area(f(xs), ws, c), rel=1e-12)
     inA, inB = f(xs) > c, f(xs + 0.1) > c
     lp = rng.normal(-1.0, 0.3, 5000)
-    assert bb.set_iou(inA, inB, lp) == pytest.approx(orc.set_iou(inA, inB, np.exp(lp)), rel=1e-12)
+    assert bb.set_iou(inA, inB, lp, ctx) == pytest.approx(orc.set_iou(inA, inB, np.exp(lp)), rel=1e-12)
     # AEConfidence.calculate: both posteriors evaluated by the fused device sweep, then the reference's quantile / IoU steps
     pr, problem = _problem(bb, ctx)
     xs = problem.x_prior.rand(6000, np.random.default_rng(8))
