@@ -72,6 +72,22 @@ int ensure_ws(Ctx* ctx, size_t bytes) {
   return 0;
 }
 
+static int ensure_pin(Ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pin_bytes) return 0;
+  if (ctx->pin) { cudaFreeHost(ctx->pin); ctx->pin = nullptr; ctx->pin_bytes = 0; }
+  BOSIP_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->pin), bytes, cudaHostAllocDefault));
+  ctx->pin_bytes = bytes;
+  return 0;
+}
+// true for plain malloc'ed host memory (not cudaHostAlloc'ed / cudaHostRegister'ed): copies from/to it are staged by the driver
+// and BLOCK the calling thread, a device-to-host copy until the producing kernels have finished
+static bool is_pageable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
 int make_like_params(Ctx* ctx, const bosip_b200_like_normal* like, int gp_p, EpiParams* ep) {
   const int q = like->p, kind = like->kind;
   if (q < 1 || q > MAX_P) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "likelihood dimension out of range");
@@ -270,6 +286,41 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   cudaStream_t sc = ctx->s_comp, si = ctx->s_in, so = ctx->s_out;
   (void)want_lv_dev;
 
+  // ---- pageable host buffers (what a Julia `Array{Float64}` is): a cudaMemcpyAsync to or from them blocks the calling thread -- a
+  // device-to-host copy until the chunk's kernels have finished -- so the launch loop could never run ahead of the GPU (measured:
+  // -6 % end to end).  They are staged through library-owned pinned double buffers instead: host memcpy user -> pinned before the
+  // H2D of chunk c, pinned -> user for chunk c-2 once its D2H event has fired; still ONE cudaMemcpyAsync per array per chunk.
+  const bool use_out = sw.use_like;
+  const bool pin_stage = host && (is_pageable(sw.xq) || is_pageable(sw.mean_at_xq) || is_pageable(sw.logprior) || is_pageable(sw.mu) ||
+                                  is_pageable(sw.var) || (use_out && (is_pageable(sw.la) || is_pageable(sw.lm) || is_pageable(sw.lv))));
+  size_t pi_x[2] = {0, 0}, pi_mean[2] = {0, 0}, pi_lp[2] = {0, 0}, po_mu[2] = {0, 0}, po_var[2] = {0, 0}, po_la[2] = {0, 0}, po_lm[2] = {0, 0},
+         po_lv[2] = {0, 0};
+  if (pin_stage) {
+    size_t poff = 0;
+    auto pcarve = [&](size_t n_doubles) { size_t o = poff; poff += (n_doubles * 8 + 255) / 256 * 256; return o; };
+    for (int b = 0; b < 2; ++b) {
+      pi_x[b] = pcarve((size_t)d * mc);
+      if (sw.mean_at_xq) pi_mean[b] = pcarve((size_t)p * mc);
+      if (sw.logprior) pi_lp[b] = pcarve((size_t)mc);
+      if (sw.mu) po_mu[b] = pcarve((size_t)p * mc);
+      if (sw.var) po_var[b] = pcarve((size_t)p * mc);
+      if (sw.la && use_out) po_la[b] = pcarve((size_t)mc);
+      if (sw.lm && use_out) po_lm[b] = pcarve((size_t)mc);
+      if (sw.lv && use_out) po_lv[b] = pcarve((size_t)mc);
+    }
+    BOSIP_TRY(ensure_pin(ctx, poff));
+  }
+  auto PIN = [&](size_t o) { return reinterpret_cast<double*>(ctx->pin + o); };
+  // copy chunk `cc`'s outputs from pinned buffer bb to the caller's arrays (its D2H event must have completed)
+  auto drain_out = [&](int64_t cc, int bb) {
+    const int64_t q0 = cc * ppc, qv = std::min(ppc, M - q0);
+    if (sw.mu) memcpy(sw.mu + (size_t)q0 * p, PIN(po_mu[bb]), (size_t)qv * p * 8);
+    if (sw.var) memcpy(sw.var + (size_t)q0 * p, PIN(po_var[bb]), (size_t)qv * p * 8);
+    if (sw.la && use_out) memcpy(sw.la + q0, PIN(po_la[bb]), (size_t)qv * 8);
+    if (sw.lm && use_out) memcpy(sw.lm + q0, PIN(po_lm[bb]), (size_t)qv * 8);
+    if (sw.lv && use_out) memcpy(sw.lv + q0, PIN(po_lv[bb]), (size_t)qv * 8);
+  };
+
   for (int64_t c = 0; c < nchunks; ++c) {
     const int b = (int)(c & 1);
     const int64_t c0 = c * ppc, mv = std::min(ppc, M - c0);
@@ -281,10 +332,21 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
       BOSIP_TRY(launch_candidates(ctx, sw.src, d, mv, sw.index_offset + c0, D(o_x[b]), sc));
       x_dev = D(o_x[b]);
     } else if (host) {
+      const double *hx = sw.xq + (size_t)c0 * d, *hmean = sw.mean_at_xq ? sw.mean_at_xq + (size_t)c0 * p : nullptr,
+                   *hlp = sw.logprior ? sw.logprior + c0 : nullptr;
+      if (pin_stage) {
+        if (c >= 2) {   // chunk c-2 used the same pinned buffers: its copies are done once its D2H event has fired
+          BOSIP_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[b]));
+          drain_out(c - 2, b);
+        }
+        memcpy(PIN(pi_x[b]), hx, (size_t)mv * d * 8); hx = PIN(pi_x[b]);
+        if (hmean) { memcpy(PIN(pi_mean[b]), hmean, (size_t)mv * p * 8); hmean = PIN(pi_mean[b]); }
+        if (hlp) { memcpy(PIN(pi_lp[b]), hlp, (size_t)mv * 8); hlp = PIN(pi_lp[b]); }
+      }
       if (c >= 2) BOSIP_CUDA(ctx, cudaStreamWaitEvent(si, ctx->ev_comp[b], 0));  // buffer b's previous consumer is done
-      BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_x[b]), sw.xq + (size_t)c0 * d, (size_t)mv * d * 8, cudaMemcpyHostToDevice, si));
-      if (sw.mean_at_xq) BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_mean[b]), sw.mean_at_xq + (size_t)c0 * p, (size_t)mv * p * 8, cudaMemcpyHostToDevice, si));
-      if (sw.logprior) BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_lpin[b]), sw.logprior + c0, (size_t)mv * 8, cudaMemcpyHostToDevice, si));
+      BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_x[b]), hx, (size_t)mv * d * 8, cudaMemcpyHostToDevice, si));
+      if (hmean) BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_mean[b]), hmean, (size_t)mv * p * 8, cudaMemcpyHostToDevice, si));
+      if (hlp) BOSIP_CUDA(ctx, cudaMemcpyAsync(D(o_lpin[b]), hlp, (size_t)mv * 8, cudaMemcpyHostToDevice, si));
       BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_in[b], si));
       BOSIP_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[b], 0));
       if (c >= 2) BOSIP_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_out[b], 0));  // output buffer b has been drained
@@ -342,13 +404,19 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     // ---------------- outputs
     if (host) {
       BOSIP_CUDA(ctx, cudaStreamWaitEvent(so, ctx->ev_comp[b], 0));
-      if (sw.mu) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.mu + (size_t)c0 * p, D(o_mu[b]), (size_t)mv * p * 8, cudaMemcpyDeviceToHost, so));
-      if (sw.var) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.var + (size_t)c0 * p, D(o_var[b]), (size_t)mv * p * 8, cudaMemcpyDeviceToHost, so));
-      if (sw.la && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.la + c0, D(o_la[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
-      if (sw.lm && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.lm + c0, D(o_lm[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
-      if (sw.lv && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(sw.lv + c0, D(o_lv[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.mu) BOSIP_CUDA(ctx, cudaMemcpyAsync(pin_stage ? PIN(po_mu[b]) : sw.mu + (size_t)c0 * p, D(o_mu[b]), (size_t)mv * p * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.var) BOSIP_CUDA(ctx, cudaMemcpyAsync(pin_stage ? PIN(po_var[b]) : sw.var + (size_t)c0 * p, D(o_var[b]), (size_t)mv * p * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.la && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(pin_stage ? PIN(po_la[b]) : sw.la + c0, D(o_la[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.lm && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(pin_stage ? PIN(po_lm[b]) : sw.lm + c0, D(o_lm[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
+      if (sw.lv && sw.use_like) BOSIP_CUDA(ctx, cudaMemcpyAsync(pin_stage ? PIN(po_lv[b]) : sw.lv + c0, D(o_lv[b]), (size_t)mv * 8, cudaMemcpyDeviceToHost, so));
     }
     BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_out[b], so));
+  }
+  if (pin_stage) {   // the last two chunks still sit in the pinned buffers
+    for (int64_t c = std::max<int64_t>(0, nchunks - 2); c < nchunks; ++c) {
+      BOSIP_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[c & 1]));
+      drain_out(c, (int)(c & 1));
+    }
   }
   unsigned long long res[8];
   BOSIP_CUDA(ctx, cudaMemcpyAsync(res, scal, sizeof(res), cudaMemcpyDeviceToHost, sc));
@@ -450,6 +518,7 @@ int bosip_b200_shutdown(bosip_b200_ctx* h) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
   for (auto& e : h->tp.pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_in[b]); cudaEventDestroy(ctx->ev_comp[b]); cudaEventDestroy(ctx->ev_out[b]); }
   cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1); cudaEventDestroy(ctx->ev_dep);

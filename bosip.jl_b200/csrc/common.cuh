@@ -86,6 +86,9 @@ struct Ctx {
   // chunk workspace (grown on demand)
   size_t ws_bytes = 0;
   char* ws = nullptr;
+  // pinned host staging for callers that hand over PAGEABLE host buffers (Julia's Array{Float64}); grown on demand
+  size_t pin_bytes = 0;
+  char* pin = nullptr;
   Timing timing;
 };
 

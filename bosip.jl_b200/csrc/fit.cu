@@ -6,10 +6,13 @@
 //   * right-looking Cholesky, NB = 64: diagonal block factorised + inverted by one CTA in shared memory,
 //     panel  L21 = A21 inv(L11)^T  and trailing update  A22 -= L21 L21^T  by a strided batched DMMA GEMM;
 //   * triangular inverse by recursive doubling: the 64x64 diagonal inverses come out of the Cholesky for free,
-//     then level s = 64,128,...: X21 = -X22 (L21 X11), two batched GEMMs per level (log2(N/64) levels);
-//   * a = Linv^T (Linv y);
+//     then level s = 64,128,...: X21 = -X22 (L21 X11), two batched GEMMs per level (ceil(log2(P/64)) levels).  Both products have
+//     a triangular factor (X11 resp. X22), so every CTA walks only the non-zero half of its k-range; a ragged last pair
+//     (P is NOT rounded to a power of two) is one more launch per level with a shorter X22;
+//   * a = K^{-1} y by two blocked triangular SOLVES with L (forward, then backward substitution; the 64x64 diagonal blocks are
+//     substituted exactly, the off-diagonal part is a GEMV) -- not through the explicit inverse;
 //   * L^{-1} scaled by alpha^2 is repacked tile-major + XOR-swizzled for the variance GEMM's bulk copies.
-// Matrices are padded to P2 = 64 * 2^ceil(log2(ceil(N/64))) with an identity tail.
+// Matrices are padded to P = 64 * ceil(N/64) with an identity tail.
 #include <math.h>
 #include <vector>
 
@@ -22,59 +25,101 @@ constexpr int NB = 64;
 constexpr size_t POTRF_SMEM = 2 * NB * (NB + 1) * sizeof(double);
 
 // ------------------------------------------------------------------------------------------------ generic GEMM
-// C(m,n) = beta*C(m,n) + alpha * sum_k A(m,k) B(k,n), every operand addressed by (row stride, col stride),
-// two-level batch (z = z1 + nb1*z2).  M,N multiples of 64, K multiple of 16.  lower_only skips tiles above the
-// diagonal (SYRK-style trailing update).  64x64 CTA tile, 4 warps x (32x32), DMMA m8n8k4.
+// C(m,n) = beta*C(m,n) + alpha * sum_k A(m,k) B(k,n), two-level batch (z = z1 + nb1*z2).  A and C are column-major (unit row
+// stride, leading dimensions sak / scn); B is addressed by (sbk, sbn) with ONE of them equal to 1 (template BK: k is the unit
+// direction).  M, N multiples of 64, K multiple of 16, every base pointer and leading dimension a multiple of 2 doubles.
+//   lower_only : skip CTA tiles that lie entirely above the diagonal (SYRK-style trailing update);
+//   b_lower    : B(k,n) = 0 for k < n  (lower-triangular right factor)  -> the k-loop starts at the tile's first column;
+//   a_lower    : A(m,k) = 0 for k > m  (lower-triangular left factor)   -> the k-loop ends at the tile's last row.
+// CTA tile 128 x 64, 8 warps x (32 x 32) of DMMA m8n8k4, k-slabs of 16 through a 3-stage cp.async ring (16-byte copies along the
+// unit-stride direction).  Shared-memory rows are padded by 4 doubles: the 8-row x 4-column fragment loads of a half-warp then
+// fall into 16 distinct bank pairs.
 struct GemmArgs {
   const double* A; const double* B; double* C;
   long long sam, sak, sbk, sbn, scm, scn;
   long long bA1, bA2, bB1, bB2, bC1, bC2;
-  int nb1, K, lower_only;
+  int nb1, K, lower_only, a_lower, b_lower, M, N;
   double alpha, beta;
 };
 
-__global__ void __launch_bounds__(128) gemm64_kernel(const __grid_constant__ GemmArgs g) {
-  if (g.lower_only && blockIdx.y > blockIdx.x) return;
-  __shared__ double sA[64][TILE_K + 4];
-  __shared__ double sB[64][TILE_K + 4];
+constexpr int GM = 128, GN = 64, GK = 16, GSTAGES = 3;
+constexpr int SA_LD = GM + 4;          // sA[k][m]
+constexpr int SB_LD_N = GN + 4;        // sB[k][n]  (B with unit n-stride)
+constexpr int SB_LD_K = GK + 4;        // sB[n][k]  (B with unit k-stride)
+constexpr int G_STAGE_DOUBLES = GK * SA_LD + GN * SB_LD_K;   // 2112 + 1280 (>= GK * SB_LD_N)
+constexpr size_t GEMM_SMEM = (size_t)GSTAGES * G_STAGE_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool BK>
+__global__ void __launch_bounds__(256) gemm_dmma_kernel(const __grid_constant__ GemmArgs g) {
+  const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
+  if (g.lower_only && n0 >= m0 + GM) return;
+  extern __shared__ __align__(16) unsigned char gemm_smem_raw[];
+  double* smem = reinterpret_cast<double*>(gemm_smem_raw);
   const int z1 = blockIdx.z % g.nb1, z2 = blockIdx.z / g.nb1;
-  const double* A = g.A + z1 * g.bA1 + z2 * g.bA2 + (long long)blockIdx.x * 64 * g.sam;
-  const double* B = g.B + z1 * g.bB1 + z2 * g.bB2 + (long long)blockIdx.y * 64 * g.sbn;
-  double* C = g.C + z1 * g.bC1 + z2 * g.bC2 + (long long)blockIdx.x * 64 * g.scm + (long long)blockIdx.y * 64 * g.scn;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tig = lane & 3;
-  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  const double* A = g.A + z1 * g.bA1 + z2 * g.bA2 + m0;
+  const double* B = g.B + z1 * g.bB1 + z2 * g.bB2 + (long long)n0 * g.sbn;
+  double* C = g.C + z1 * g.bC1 + z2 * g.bC2 + m0 + (long long)n0 * g.scn;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const bool m_hi_valid = m0 + 64 < g.M;            // M is a multiple of 64: the upper half of the tile is all-or-nothing
+  int k_lo = 0, k_hi = g.K;
+  if (g.b_lower) k_lo = n0 & ~(GK - 1);
+  if (g.a_lower) k_hi = min(g.K, m0 + (m_hi_valid ? GM : 64));
+  const int nk = (k_hi - k_lo + GK - 1) / GK;
+
+  auto load_slab = [&](int kt, int stage) {
+    double* sA = smem + (size_t)stage * G_STAGE_DOUBLES;
+    double* sB = sA + GK * SA_LD;
+    const int k0 = k_lo + kt * GK;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {          // A: 128 m x 16 k = 1024 chunks of 2 doubles
+      const int c = tid + it * 256, k = c >> 6, m2 = (c & 63) << 1;
+      if (m2 < 64 || m_hi_valid) cp_async16(sA + k * SA_LD + m2, A + m2 + (long long)(k0 + k) * g.sak);
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {          // B: 64 n x 16 k = 512 chunks
+      const int c = tid + it * 256;
+      if (BK) { const int n = c >> 3, k2 = (c & 7) << 1; cp_async16(sB + n * SB_LD_K + k2, B + (k0 + k2) + (long long)n * g.sbn); }
+      else { const int k = c >> 5, n2 = (c & 31) << 1; cp_async16(sB + k * SB_LD_N + n2, B + (long long)(k0 + k) * g.sbk + n2); }
+    }
+  };
+
   double c[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn) { c[i][jn][0] = 0.0; c[i][jn][1] = 0.0; }
 
-  for (int k0 = 0; k0 < g.K; k0 += TILE_K) {
-    // cooperative load of a 64 x 16 slab of A and of B^T (row = m resp. n, col = k)
-    for (int e = threadIdx.x; e < 64 * TILE_K; e += 128) {
-      // pick the thread->element map so that the unit-stride direction is walked by consecutive threads
-      int r, kk;
-      if (g.sam == 1) { r = e & 63; kk = e >> 6; } else { kk = e & 15; r = e >> 4; }
-      sA[r][kk] = A[(long long)r * g.sam + (long long)(k0 + kk) * g.sak];
-      int rb, kb;
-      if (g.sbn == 1) { rb = e & 63; kb = e >> 6; } else { kb = e & 15; rb = e >> 4; }
-      sB[rb][kb] = B[(long long)(k0 + kb) * g.sbk + (long long)rb * g.sbn];
-    }
-    __syncthreads();
 #pragma unroll
-    for (int ks = 0; ks < TILE_K; ks += 4) {
+  for (int s = 0; s < GSTAGES - 1; ++s) { if (s < nk) load_slab(s, s); cp_async_commit(); }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();                             // slab kt has landed for every thread; slab kt-1's readers are done
+    if (kt + GSTAGES - 1 < nk) load_slab(kt + GSTAGES - 1, (kt + GSTAGES - 1) % GSTAGES);
+    cp_async_commit();
+    const double* sA = smem + (size_t)(kt % GSTAGES) * G_STAGE_DOUBLES;
+    const double* sB = sA + GK * SA_LD;
+#pragma unroll
+    for (int ks = 0; ks < GK; ks += 4) {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[wm + 8 * i + gq][ks + tig];
+      for (int i = 0; i < 4; ++i) a[i] = sA[(ks + tig) * SA_LD + wm + 8 * i + gq];
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn) b[jn] = sB[wn + 8 * jn + gq][ks + tig];
+      for (int jn = 0; jn < 4; ++jn) b[jn] = BK ? sB[(wn + 8 * jn + gq) * SB_LD_K + ks + tig] : sB[(ks + tig) * SB_LD_N + wn + 8 * jn + gq];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int jn = 0; jn < 4; ++jn) dmma884(c[i][jn][0], c[i][jn][1], a[i], b[jn]);
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  if (wm >= 64 && !m_hi_valid) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -82,16 +127,24 @@ __global__ void __launch_bounds__(128) gemm64_kernel(const __grid_constant__ Gem
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const long long m = wm + 8 * i + gq, n = wn + 8 * jn + 2 * tig + h;
-        double* dst = C + m * g.scm + n * g.scn;
+        double* dst = C + m + n * g.scn;
         const double v = g.alpha * c[i][jn][h];
         *dst = (g.beta == 0.0) ? v : fma(g.beta, *dst, v);
       }
 }
 
-static int gemm64(Ctx* ctx, const GemmArgs& g, int M, int N, int batch, cudaStream_t st) {
+static int gemm64(Ctx* ctx, GemmArgs g, int M, int N, int batch, cudaStream_t st) {
   if (M <= 0 || N <= 0 || batch <= 0) return 0;
-  dim3 grid((unsigned)(M / 64), (unsigned)(N / 64), (unsigned)batch);
-  gemm64_kernel<<<grid, 128, 0, st>>>(g);
+  g.M = M; g.N = N;
+  if (g.sam != 1 || g.scm != 1 || (g.sbk != 1 && g.sbn != 1)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "gemm: unsupported operand layout");
+  dim3 grid((unsigned)((M + GM - 1) / GM), (unsigned)(N / GN), (unsigned)batch);
+  if (g.sbk == 1) {   // the attribute is per device: set it on every launch (a host-side table write)
+    BOSIP_CUDA(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    gemm_dmma_kernel<true><<<grid, 256, GEMM_SMEM, st>>>(g);
+  } else {
+    BOSIP_CUDA(ctx, cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    gemm_dmma_kernel<false><<<grid, 256, GEMM_SMEM, st>>>(g);
+  }
   BOSIP_CUDA(ctx, cudaGetLastError());
   return 0;
 }
@@ -175,27 +228,74 @@ __global__ void __launch_bounds__(64) potrf_diag_kernel(double* __restrict__ Ap,
   for (int c = 0; c < NB; ++c) X[tid + (size_t)c * P2] = x[tid][c];
 }
 
-// w = Linv y (lower), thread per row
-__global__ void trmv_lower_kernel(const double* __restrict__ Xp, int P2, int N, const double* __restrict__ y,
-                                  double* __restrict__ w) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  if (r >= N) return;
-  const double* X = Xp + (size_t)j * P2 * P2;
-  double acc = 0.0;
-  for (int k = 0; k <= r; ++k) acc = fma(X[(size_t)r + (size_t)k * P2], y[(size_t)j * N + k], acc);
-  w[(size_t)j * N + r] = acc;
-}
-// a = Linv^T w, warp per column
-__global__ void trmv_lower_T_kernel(const double* __restrict__ Xp, int P2, int N, const double* __restrict__ w,
-                                    double* __restrict__ a) {
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31, j = blockIdx.y;
-  if (c >= N) return;
-  const double* X = Xp + (size_t)j * P2 * P2 + (size_t)c * P2;
-  double acc = 0.0;
-  for (int r = c + lane; r < N; r += 32) acc = fma(X[r], w[(size_t)j * N + r], acc);
+// a = K^{-1} y = L^{-T} (L^{-1} y) by two blocked triangular solves with the Cholesky factor itself (not through the explicit
+// inverse).  One CTA of 256 threads per output; 64-row blocks: the off-diagonal part is a GEMV with coalesced column reads, the
+// 64 x 64 diagonal block is substituted exactly by warp 0 (two rows per lane, the pivot row's value broadcast by shuffle).
+__global__ void __launch_bounds__(256) trsv_chol_kernel(const double* __restrict__ Lp, int P, int N, const double* __restrict__ y,
+                                                        double* __restrict__ w_out, double* __restrict__ a_out) {
+  extern __shared__ __align__(16) unsigned char trsv_smem[];
+  double* w = reinterpret_cast<double*>(trsv_smem);     // [P]   forward solution, then overwritten by the backward one
+  double (*part)[64] = reinterpret_cast<double (*)[64]>(w + P);   // [4][64] GEMV partials
+  double* r = &part[0][0] + 4 * 64;                     // [64]  right-hand side of the diagonal block
+  double (*D)[65] = reinterpret_cast<double (*)[65]>(r + 64);     // [64][65] diagonal block
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* L = Lp + (size_t)j * P * P;
+  const int nb = P / 64;
+  // ---------------- forward: L w = y
+  for (int b = 0; b < nb; ++b) {
+    const int r0 = b * 64, row = tid & 63, q = tid >> 6;
+    double acc = 0.0;
+    for (int c = q; c < r0; c += 4) acc = fma(L[(size_t)(r0 + row) + (size_t)c * P], w[c], acc);
+    part[q][row] = acc;
+    for (int e = tid; e < 64 * 64; e += 256) { const int rr = e & 63, cc = e >> 6; D[rr][cc] = L[(size_t)(r0 + rr) + (size_t)(r0 + cc) * P]; }
+    __syncthreads();
+    if (tid < 64) {
+      const double yv = (r0 + tid < N) ? y[(size_t)j * N + r0 + tid] : 0.0;
+      r[tid] = yv - (((part[0][tid] + part[1][tid]) + part[2][tid]) + part[3][tid]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double x0 = r[lane], x1 = r[lane + 32];
+      for (int k = 0; k < 64; ++k) {
+        const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
+        const double wk = rk / D[k][k];
+        if (lane == (k & 31)) { if (k < 32) x0 = wk; else x1 = wk; }
+        if (lane > k) x0 = fma(-D[lane][k], wk, x0);
+        if (lane + 32 > k) x1 = fma(-D[lane + 32][k], wk, x1);
+      }
+      w[r0 + lane] = x0; w[r0 + lane + 32] = x1;
+    }
+    __syncthreads();
+  }
+  if (w_out) for (int e = tid; e < N; e += 256) w_out[(size_t)j * N + e] = w[e];
+  // ---------------- backward: L^T a = w  (w is overwritten block by block from the end)
+  for (int b = nb - 1; b >= 0; --b) {
+    const int r0 = b * 64;
+    // r[col] = w[r0 + col] - sum_{c >= r0 + 64} L[c][r0 + col] a[c]: warp `warp` owns columns warp, warp + 8, ..., lanes run along c
+    for (int col = warp; col < 64; col += 8) {
+      double acc = 0.0;
+      const double* Lc = L + (size_t)(r0 + col) * P;
+      for (int c = r0 + 64 + lane; c < P; c += 32) acc = fma(Lc[c], w[c], acc);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) a[(size_t)j * N + c] = acc;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) r[col] = w[r0 + col] - acc;
+    }
+    for (int e = tid; e < 64 * 64; e += 256) { const int rr = e & 63, cc = e >> 6; D[rr][cc] = L[(size_t)(r0 + rr) + (size_t)(r0 + cc) * P]; }
+    __syncthreads();
+    if (warp == 0) {
+      double x0 = r[lane], x1 = r[lane + 32];
+      for (int k = 63; k >= 0; --k) {
+        const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
+        const double ak = rk / D[k][k];
+        if (lane == (k & 31)) { if (k < 32) x0 = ak; else x1 = ak; }
+        if (lane < k) x0 = fma(-D[k][lane], ak, x0);          // column `lane` of L^T row k = L[k][lane]
+        if (lane + 32 < k) x1 = fma(-D[k][lane + 32], ak, x1);
+      }
+      w[r0 + lane] = x0; w[r0 + lane + 32] = x1;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < N; e += 256) a_out[(size_t)j * N + e] = w[e];
 }
 
 // LinvT[j][t][kc][r][swz] = alpha_j^2 Linv[128 t + r][16 kc + kk]
@@ -237,11 +337,7 @@ void gp_destroy(Gp* gp) {
   delete gp;
 }
 
-static int padded_pow2(int N) {
-  int blocks = (N + NB - 1) / NB, b = 1;
-  while (b < blocks) b <<= 1;
-  return b * NB;
-}
+static int padded_size(int N) { return (N + NB - 1) / NB * NB; }   // multiple of 64, NOT a power of two
 
 int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, const double* Y, const double* lambda,
              const double* alpha, const double* sigma, const double* mean_at_X, const double* L_host,
@@ -264,7 +360,7 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   gp->Ns = (int)round_up(N, TILE_K); gp->T = (N + TILE_N - 1) / TILE_N; gp->KC = gp->Ns / TILE_K;
   bosip_b200_gp_opts dflt = {0.0, 0, 1};
   gp->opts = opts_in ? *opts_in : dflt;
-  const int dp = gp->dp, Ns = gp->Ns, T = gp->T, KC = gp->KC, P2 = padded_pow2(N);
+  const int dp = gp->dp, Ns = gp->Ns, T = gp->T, KC = gp->KC, P2 = padded_size(N);
   cudaStream_t st = ctx->s_comp;
   struct Guard { Gp* g; bool ok = false; ~Guard() { if (!ok) gp_destroy(g); } } guard{gp};
 
@@ -360,33 +456,55 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     BOSIP_FAIL(ctx, BOSIP_B200_ENOTPD, "Cholesky: non-positive pivot in diagonal block " + std::to_string(h_flag - 1) +
                                          " (matrix is not positive definite)");
 
-  // ---- triangular inverse by recursive doubling: X21 = -X22 (L21 X11)
+  // ---- triangular inverse by recursive doubling: X21 = -X22 (L21 X11).  Level s pairs block [2is, 2is+s) with
+  //      [2is+s, 2is+2s); when P2 is not a multiple of 2s the last pair's second block is shorter (m rows) -- one more launch.
   if (nb > 1) {
-    BOSIP_CUDA(ctx, cudaMalloc(&Tmp, (size_t)p * (P2 / 2) * (P2 / 2) * 8 * 2));  // >= (P2/(2s)) s^2 per output
+    BOSIP_CUDA(ctx, cudaMalloc(&Tmp, (size_t)p * ((size_t)P2 * P2 / 2 + (size_t)64 * P2) * 8));
     for (int s = NB; s < P2; s <<= 1) {
       const int npairs = P2 / (2 * s);
       const long long pair_stride = (long long)2 * s * (P2 + 1);
+      const long long r_off = (long long)npairs * 2 * s;                 // first row of the ragged pair
+      const int m_rag = (P2 - r_off > s) ? (int)(P2 - r_off - s) : 0;    // rows of its X22 (multiple of 64)
+      double* Tmp_rag = Tmp + (size_t)p * npairs * s * s;
       GemmArgs g{};
-      g.nb1 = npairs; g.K = s; g.lower_only = 0;
-      // T = L21 X11
-      g.A = Lp + s; g.sam = 1; g.sak = P2; g.bA1 = pair_stride; g.bA2 = (long long)P2 * P2;
-      g.B = Xp; g.sbk = 1; g.sbn = P2; g.bB1 = pair_stride; g.bB2 = (long long)P2 * P2;
-      g.C = Tmp; g.scm = 1; g.scn = s; g.bC1 = (long long)s * s; g.bC2 = (long long)npairs * s * s;
-      g.alpha = 1.0; g.beta = 0.0;
-      BOSIP_TRY(gemm64(ctx, g, s, s, npairs * p, st));
-      // X21 = -X22 T
-      g.A = Xp + (long long)s * (P2 + 1); g.sam = 1; g.sak = P2; g.bA1 = pair_stride; g.bA2 = (long long)P2 * P2;
-      g.B = Tmp; g.sbk = 1; g.sbn = s; g.bB1 = (long long)s * s; g.bB2 = (long long)npairs * s * s;
-      g.C = Xp + s; g.scm = 1; g.scn = P2; g.bC1 = pair_stride; g.bC2 = (long long)P2 * P2;
-      g.alpha = -1.0; g.beta = 0.0;
-      BOSIP_TRY(gemm64(ctx, g, s, s, npairs * p, st));
+      g.K = s; g.lower_only = 0;
+      if (npairs > 0) {
+        g.nb1 = npairs;
+        // T = L21 X11   (X11 lower triangular: k >= n)
+        g.A = Lp + s; g.sam = 1; g.sak = P2; g.bA1 = pair_stride; g.bA2 = (long long)P2 * P2;
+        g.B = Xp; g.sbk = 1; g.sbn = P2; g.bB1 = pair_stride; g.bB2 = (long long)P2 * P2;
+        g.C = Tmp; g.scm = 1; g.scn = s; g.bC1 = (long long)s * s; g.bC2 = (long long)npairs * s * s;
+        g.alpha = 1.0; g.beta = 0.0; g.a_lower = 0; g.b_lower = 1;
+        BOSIP_TRY(gemm64(ctx, g, s, s, npairs * p, st));
+        // X21 = -X22 T  (X22 lower triangular: k <= m)
+        g.A = Xp + (long long)s * (P2 + 1); g.sam = 1; g.sak = P2; g.bA1 = pair_stride; g.bA2 = (long long)P2 * P2;
+        g.B = Tmp; g.sbk = 1; g.sbn = s; g.bB1 = (long long)s * s; g.bB2 = (long long)npairs * s * s;
+        g.C = Xp + s; g.scm = 1; g.scn = P2; g.bC1 = pair_stride; g.bC2 = (long long)P2 * P2;
+        g.alpha = -1.0; g.beta = 0.0; g.a_lower = 1; g.b_lower = 0;
+        BOSIP_TRY(gemm64(ctx, g, s, s, npairs * p, st));
+      }
+      if (m_rag > 0) {
+        g.nb1 = 1;
+        g.A = Lp + (r_off + s) + r_off * P2; g.sam = 1; g.sak = P2; g.bA1 = 0; g.bA2 = (long long)P2 * P2;
+        g.B = Xp + r_off * (P2 + 1); g.sbk = 1; g.sbn = P2; g.bB1 = 0; g.bB2 = (long long)P2 * P2;
+        g.C = Tmp_rag; g.scm = 1; g.scn = m_rag; g.bC1 = 0; g.bC2 = (long long)m_rag * s;
+        g.K = s; g.alpha = 1.0; g.beta = 0.0; g.a_lower = 0; g.b_lower = 1;
+        BOSIP_TRY(gemm64(ctx, g, m_rag, s, p, st));
+        g.A = Xp + (r_off + s) * (P2 + 1); g.sam = 1; g.sak = P2; g.bA1 = 0; g.bA2 = (long long)P2 * P2;
+        g.B = Tmp_rag; g.sbk = 1; g.sbn = m_rag; g.bB1 = 0; g.bB2 = (long long)m_rag * s;
+        g.C = Xp + (r_off + s) + r_off * P2; g.scm = 1; g.scn = P2; g.bC1 = 0; g.bC2 = (long long)P2 * P2;
+        g.K = m_rag; g.alpha = -1.0; g.beta = 0.0; g.a_lower = 1; g.b_lower = 0;
+        BOSIP_TRY(gemm64(ctx, g, m_rag, s, p, st));
+      }
     }
   }
 
-  // ---- weights a = K^{-1} y = Linv^T (Linv y)
+  // ---- weights a = K^{-1} y: forward + backward substitution with L (trsv_chol_kernel)
   if (!L_host) {
-    trmv_lower_kernel<<<dim3((N + 127) / 128, p), 128, 0, st>>>(Xp, P2, N, dY, dW);
-    trmv_lower_T_kernel<<<dim3((N + 3) / 4, p), 128, 0, st>>>(Xp, P2, N, dW, gp->a);
+    const size_t trsv_smem = ((size_t)P2 + 4 * 64 + 64 + 64 * 65) * sizeof(double);
+    if (trsv_smem > 220 * 1024) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "N too large for the in-shared-memory triangular solve (N <= 23000)");
+    BOSIP_CUDA(ctx, cudaFuncSetAttribute(trsv_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv_smem));
+    trsv_chol_kernel<<<p, 256, trsv_smem, st>>>(Lp, P2, N, dY, dW, gp->a);
     BOSIP_CUDA(ctx, cudaGetLastError());
   } else {
     // a_host is N x p column-major == [p][N]

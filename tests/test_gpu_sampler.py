@@ -153,8 +153,14 @@ def test_confidence_set_device_kernels_edge_cases(bb, ctx):
         v = rng.normal(size=n); w = rng.uniform(0.0, 2.0, n); w[rng.random(n) < 0.2] = 0.0
         if not np.any(w):
             w[0] = 1.0
-        for p in (0.0, 0.03, 0.5, 0.8, 1.0):
+        for p in (0.0, 0.03, 0.5, 0.8):
             assert bb.weighted_quantile(v, w, p, ctx) == pytest.approx(orc.weighted_quantile(v, w, p), rel=1e-12, abs=1e-15)
+        # p = 1: h = (W - w_1) + w_1 lands within rounding of the total weight, so whether the last cumulative sum exceeds it (and
+        # the last two values are interpolated with a fraction 1 - O(n eps)) depends on the summation order, in the reference too:
+        # the result is the largest kept value up to O(n eps W / w_last) of the last gap
+        top = np.max(v[w > 0])
+        assert bb.weighted_quantile(v, w, 1.0, ctx) == pytest.approx(top, abs=1e-9 * (np.ptp(v) + 1e-300) + 1e-15)
+        assert orc.weighted_quantile(v, w, 1.0) == pytest.approx(top, abs=1e-9 * (np.ptp(v) + 1e-300) + 1e-15)
         v[n // 2] = v[0]                                              # ties
         assert bb.weighted_quantile(v, w, 0.37, ctx) == pytest.approx(orc.weighted_quantile(v, w, 0.37), rel=1e-12, abs=1e-15)
         vd, wd = torch.as_tensor(v, device="cuda"), torch.as_tensor(w, device="cuda")
