@@ -51,6 +51,7 @@ struct Gp {
   Ctx* ctx;
   int kernel_id, d, dp, N, Ns, p, T, KC;
   bosip_b200_gp_opts opts;
+  void* block = nullptr;    // the one device allocation that holds Us .. a
   double* Us = nullptr;     // [p][dp][Ns]  training inputs scaled by c_kernel / lambda_j (SoA, zero padded)
   double* scale = nullptr;  // [p][dp]      c_kernel / lambda_jk (0 for padded dims)
   double* As = nullptr;     // [p][Ns]      alpha_j^2 * a_j (zero padded)

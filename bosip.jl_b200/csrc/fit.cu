@@ -14,6 +14,9 @@
 //   * L^{-1} scaled by alpha^2 is repacked tile-major + XOR-swizzled for the variance GEMM's bulk copies.
 // Matrices are padded to P = 64 * ceil(N/64) with an identity tail.
 #include <math.h>
+#include <stdlib.h>
+#include <time.h>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -188,114 +191,141 @@ __global__ void pad_L_kernel(const double* __restrict__ Lin, int N, int P2, doub
 }
 
 // Factorise the 64x64 diagonal block b in place (lower), zero its strict upper part, and write its inverse into the
-// same block of Xp.  One CTA of 64 threads per output.  flag[0] = 1 + block index on a non-positive pivot.
-__global__ void __launch_bounds__(64) potrf_diag_kernel(double* __restrict__ Ap, double* __restrict__ Xp, int P2, int b,
-                                                        int do_factor, int* __restrict__ flag) {
+// same block of Xp.  One CTA of 256 threads per output; both halves are right-looking rank-1 sweeps over shared memory with the
+// trailing region spread over all threads (two barriers per column).  flag[0] = 1 + block index on a non-positive pivot.
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap, double* __restrict__ Xp, int P2, int b,
+                                                         int do_factor, int* __restrict__ flag) {
   extern __shared__ __align__(16) unsigned char potrf_smem[];
   double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
   double (*x)[NB + 1] = s + NB;
-  const int j = blockIdx.x, tid = threadIdx.x;
+  __shared__ double diag[NB];
+  const int j = blockIdx.x, tid = threadIdx.x, tr = tid & 63, tq = tid >> 6;
   double* A = Ap + (size_t)j * P2 * P2 + (size_t)b * NB + (size_t)b * NB * P2;
-  for (int c = 0; c < NB; ++c) s[tid][c] = A[tid + (size_t)c * P2];
+  for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; s[rr][cc] = A[rr + (size_t)cc * P2]; }
   __syncthreads();
   if (do_factor) {
+    bool ok = true;
     for (int c = 0; c < NB; ++c) {
       const double piv = s[c][c];
-      if (!(piv > 0.0)) { if (tid == 0) atomicCAS(flag, 0, 1 + b); break; }  // uniform: every thread reads the same pivot
+      if (!(piv > 0.0)) { if (tid == 0) atomicCAS(flag, 0, 1 + b); ok = false; break; }  // uniform: every thread reads the same pivot
       const double lcc = sqrt(piv);
+      if (tid == c) diag[c] = lcc;
+      if (tq == 0 && tr > c) s[tr][c] = s[tr][c] / lcc;            // column c of L (the pivot itself stays in place until the write-back)
       __syncthreads();
-      if (tid == c) s[c][c] = lcc;
-      else if (tid > c) s[tid][c] = s[tid][c] / lcc;
-      __syncthreads();
-      // rank-1 update of the trailing lower triangle: row tid, columns c+1..tid
-      if (tid > c) {
-        const double l_rc = s[tid][c];
-        for (int cc = c + 1; cc <= tid; ++cc) s[tid][cc] -= l_rc * s[cc][c];
+      // rank-1 update of the trailing lower triangle: row tr, columns c+1+tq, c+5+tq, ... <= tr
+      if (tr > c) {
+        const double l_rc = s[tr][c];
+        for (int cc = c + 1 + tq; cc <= tr; cc += 4) s[tr][cc] -= l_rc * s[cc][c];
       }
       __syncthreads();
     }
-    for (int c = 0; c < NB; ++c) A[tid + (size_t)c * P2] = (c <= tid) ? s[tid][c] : 0.0;
+    if (ok) {
+      for (int e = tid; e < NB * NB; e += 256) {
+        const int rr = e & 63, cc = e >> 6;
+        A[rr + (size_t)cc * P2] = cc < rr ? s[rr][cc] : (cc == rr ? diag[rr] : 0.0);
+      }
+    }
+    __syncthreads();
+    if (tid < NB) s[tid][tid] = ok ? diag[tid] : 1.0;
+    __syncthreads();
   }
+  // inverse: solve L X = I column-block-wise as 64 rank-1 sweeps: X[k][:] = B[k][:] / L[k][k], then B[i][:] -= L[i][k] X[k][:]
+  // for the rows below (only columns <= k of row k are non-zero)
+  for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; x[rr][cc] = rr == cc ? 1.0 : 0.0; }
   __syncthreads();
-  // inverse by forward substitution, thread = column of the identity
-  for (int r = 0; r < NB; ++r) {
-    double acc = (r == tid) ? 1.0 : 0.0;
-    for (int k = tid; k < r; ++k) acc -= s[r][k] * x[k][tid];
-    x[r][tid] = (r >= tid) ? acc / s[r][r] : 0.0;
+  for (int k = 0; k < NB; ++k) {
+    const double dkk = s[k][k];
+    if (tq == 0 && tr <= k) x[k][tr] = x[k][tr] / dkk;
+    __syncthreads();
+    // rows i = k+1 .. 63 (index tr), columns jj = tq, tq+4, ... <= k
+    if (tr > k) {
+      const double l_ik = s[tr][k];
+      for (int jj = tq; jj <= k; jj += 4) x[tr][jj] -= l_ik * x[k][jj];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   double* X = Xp + (size_t)j * P2 * P2 + (size_t)b * NB + (size_t)b * NB * P2;
-  for (int c = 0; c < NB; ++c) X[tid + (size_t)c * P2] = x[tid][c];
+  for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; X[rr + (size_t)cc * P2] = cc <= rr ? x[rr][cc] : 0.0; }
 }
 
-// a = K^{-1} y = L^{-T} (L^{-1} y) by two blocked triangular solves with the Cholesky factor itself (not through the explicit
-// inverse).  One CTA of 256 threads per output; 64-row blocks: the off-diagonal part is a GEMV with coalesced column reads, the
-// 64 x 64 diagonal block is substituted exactly by warp 0 (two rows per lane, the pivot row's value broadcast by shuffle).
-__global__ void __launch_bounds__(256) trsv_chol_kernel(const double* __restrict__ Lp, int P, int N, const double* __restrict__ y,
-                                                        double* __restrict__ w_out, double* __restrict__ a_out) {
-  extern __shared__ __align__(16) unsigned char trsv_smem[];
-  double* w = reinterpret_cast<double*>(trsv_smem);     // [P]   forward solution, then overwritten by the backward one
-  double (*part)[64] = reinterpret_cast<double (*)[64]>(w + P);   // [4][64] GEMV partials
-  double* r = &part[0][0] + 4 * 64;                     // [64]  right-hand side of the diagonal block
-  double (*D)[65] = reinterpret_cast<double (*)[65]>(r + 64);     // [64][65] diagonal block
-  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// a = K^{-1} y = L^{-T} (L^{-1} y) by two blocked triangular SOLVES with the Cholesky factor itself (not through the explicit
+// inverse).  One launch per 64-row block and direction, all outputs batched: every CTA substitutes the 64 x 64 diagonal system
+// exactly (warp 0: two rows per lane, the pivot row's value broadcast by shuffle, true divisions -- redundant across CTAs, which
+// costs nothing but keeps the step to ONE kernel), CTA 0 stores the block's solution, CTA c >= 1 applies the block's solution
+// to its share of the remaining right-hand side (a GEMV slab with coalesced reads).  rhs is [p][P], zero padded.
+__device__ __forceinline__ void trsv_load_block(const double* __restrict__ L, int P, int r0, double (*D)[65]) {
+  for (int e = threadIdx.x; e < 64 * 64; e += 256) { const int rr = e & 63, cc = e >> 6; D[rr][cc] = L[(size_t)(r0 + rr) + (size_t)(r0 + cc) * P]; }
+}
+__global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ Lp, int P, int b, double* __restrict__ rhs) {
+  __shared__ double D[64][65];
+  __shared__ double w[64];
+  const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r0 = b * 64;
   const double* L = Lp + (size_t)j * P * P;
-  const int nb = P / 64;
-  // ---------------- forward: L w = y
-  for (int b = 0; b < nb; ++b) {
-    const int r0 = b * 64, row = tid & 63, q = tid >> 6;
-    double acc = 0.0;
-    for (int c = q; c < r0; c += 4) acc = fma(L[(size_t)(r0 + row) + (size_t)c * P], w[c], acc);
-    part[q][row] = acc;
-    for (int e = tid; e < 64 * 64; e += 256) { const int rr = e & 63, cc = e >> 6; D[rr][cc] = L[(size_t)(r0 + rr) + (size_t)(r0 + cc) * P]; }
-    __syncthreads();
-    if (tid < 64) {
-      const double yv = (r0 + tid < N) ? y[(size_t)j * N + r0 + tid] : 0.0;
-      r[tid] = yv - (((part[0][tid] + part[1][tid]) + part[2][tid]) + part[3][tid]);
+  double* y = rhs + (size_t)j * P;
+  trsv_load_block(L, P, r0, D);
+  __syncthreads();
+  if (warp == 0) {
+    double x0 = y[r0 + lane], x1 = y[r0 + lane + 32];
+    for (int k = 0; k < 64; ++k) {
+      const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
+      const double wk = rk / D[k][k];
+      if (lane == (k & 31)) { if (k < 32) x0 = wk; else x1 = wk; }
+      if (lane > k) x0 = fma(-D[lane][k], wk, x0);
+      if (lane + 32 > k) x1 = fma(-D[lane + 32][k], wk, x1);
     }
-    __syncthreads();
-    if (warp == 0) {
-      double x0 = r[lane], x1 = r[lane + 32];
-      for (int k = 0; k < 64; ++k) {
-        const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
-        const double wk = rk / D[k][k];
-        if (lane == (k & 31)) { if (k < 32) x0 = wk; else x1 = wk; }
-        if (lane > k) x0 = fma(-D[lane][k], wk, x0);
-        if (lane + 32 > k) x1 = fma(-D[lane + 32][k], wk, x1);
-      }
-      w[r0 + lane] = x0; w[r0 + lane + 32] = x1;
-    }
-    __syncthreads();
+    w[lane] = x0; w[lane + 32] = x1;
   }
-  if (w_out) for (int e = tid; e < N; e += 256) w_out[(size_t)j * N + e] = w[e];
-  // ---------------- backward: L^T a = w  (w is overwritten block by block from the end)
-  for (int b = nb - 1; b >= 0; --b) {
-    const int r0 = b * 64;
-    // r[col] = w[r0 + col] - sum_{c >= r0 + 64} L[c][r0 + col] a[c]: warp `warp` owns columns warp, warp + 8, ..., lanes run along c
-    for (int col = warp; col < 64; col += 8) {
-      double acc = 0.0;
-      const double* Lc = L + (size_t)(r0 + col) * P;
-      for (int c = r0 + 64 + lane; c < P; c += 32) acc = fma(Lc[c], w[c], acc);
+  __syncthreads();
+  if (blockIdx.x == 0) { if (tid < 64) y[r0 + tid] = w[tid]; return; }
+  const int row = r0 + 64 + (blockIdx.x - 1) * 256 + tid;
+  if (row >= P) return;
+  const double* Lr = L + (size_t)row + (size_t)r0 * P;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < 64; ++k) acc = fma(Lr[(size_t)k * P], w[k], acc);
+  y[row] -= acc;
+}
+__global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ Lp, int P, int b, double* __restrict__ rhs) {
+  __shared__ double D[64][65];
+  __shared__ double a[64];
+  const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r0 = b * 64;
+  const double* L = Lp + (size_t)j * P * P;
+  double* w = rhs + (size_t)j * P;
+  trsv_load_block(L, P, r0, D);
+  __syncthreads();
+  if (warp == 0) {
+    double x0 = w[r0 + lane], x1 = w[r0 + lane + 32];
+    for (int k = 63; k >= 0; --k) {
+      const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
+      const double ak = rk / D[k][k];
+      if (lane == (k & 31)) { if (k < 32) x0 = ak; else x1 = ak; }
+      if (lane < k) x0 = fma(-D[k][lane], ak, x0);          // column `lane` of row k of L^T = L[k][lane]
+      if (lane + 32 < k) x1 = fma(-D[k][lane + 32], ak, x1);
+    }
+    a[lane] = x0; a[lane + 32] = x1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) { if (tid < 64) w[r0 + tid] = a[tid]; return; }
+  // rows jj < r0 of the transposed system: w[jj] -= sum_k L[r0 + k][jj] a[k]; one warp per row, lanes along k (contiguous in memory)
+  const double a0 = a[lane], a1 = a[lane + 32];
+  for (int q = 0; q < 8; ++q) {
+    const int jj = (blockIdx.x - 1) * 64 + warp * 8 + q;
+    if (jj >= r0) break;
+    const double* Lc = L + (size_t)r0 + (size_t)jj * P;
+    double acc = fma(Lc[lane], a0, Lc[lane + 32] * a1);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) r[col] = w[r0 + col] - acc;
-    }
-    for (int e = tid; e < 64 * 64; e += 256) { const int rr = e & 63, cc = e >> 6; D[rr][cc] = L[(size_t)(r0 + rr) + (size_t)(r0 + cc) * P]; }
-    __syncthreads();
-    if (warp == 0) {
-      double x0 = r[lane], x1 = r[lane + 32];
-      for (int k = 63; k >= 0; --k) {
-        const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
-        const double ak = rk / D[k][k];
-        if (lane == (k & 31)) { if (k < 32) x0 = ak; else x1 = ak; }
-        if (lane < k) x0 = fma(-D[k][lane], ak, x0);          // column `lane` of L^T row k = L[k][lane]
-        if (lane + 32 < k) x1 = fma(-D[k][lane + 32], ak, x1);
-      }
-      w[r0 + lane] = x0; w[r0 + lane + 32] = x1;
-    }
-    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) w[jj] -= acc;
   }
-  for (int e = tid; e < N; e += 256) a_out[(size_t)j * N + e] = w[e];
+}
+// rhs[j][n] = y[j][n] for n < N, 0 for the padding rows
+__global__ void pad_rhs_kernel(const double* __restrict__ y, int N, int P, double* __restrict__ rhs) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (n < P) rhs[(size_t)j * P + n] = n < N ? y[(size_t)j * N + n] : 0.0;
+}
+__global__ void unpad_rhs_kernel(const double* __restrict__ rhs, int N, int P, double* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (n < N) out[(size_t)j * N + n] = rhs[(size_t)j * P + n];
 }
 
 // LinvT[j][t][kc][r][swz] = alpha_j^2 Linv[128 t + r][16 kc + kk]
@@ -331,8 +361,7 @@ __global__ void unpad_kernel(const double* __restrict__ Pp, int P2, int N, doubl
 // ------------------------------------------------------------------------------------------------ driver
 void gp_destroy(Gp* gp) {
   if (!gp) return;
-  cudaFree(gp->Us); cudaFree(gp->scale); cudaFree(gp->As); cudaFree(gp->LinvT);
-  cudaFree(gp->L); cudaFree(gp->Linv); cudaFree(gp->a);
+  cudaFree(gp->block);   // Us, scale, As, LinvT, L, Linv, a live in one allocation
   cudaFree(gp->LinvI8); cudaFree(gp->cscale);
   delete gp;
 }
@@ -354,6 +383,13 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     for (int k = 0; k < d; ++k)
       if (!(lambda[k + d * j] > 0.0)) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "length-scales must be > 0");
   }
+
+  // BOSIP_B200_FIT_TRACE=1: stage wall times (stream synchronised at every mark) on stderr -- development aid
+  static const bool trace = getenv("BOSIP_B200_FIT_TRACE") != nullptr;
+  std::vector<std::pair<const char*, double>> marks;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  const double t_begin = trace ? now() : 0.0;
+  auto mark = [&](const char* name) { if (trace) { cudaStreamSynchronize(ctx->s_comp); marks.emplace_back(name, now()); } };
 
   Gp* gp = new Gp();
   gp->ctx = ctx; gp->kernel_id = kernel_id; gp->d = d; gp->dp = pad_dim(d); gp->N = N; gp->p = p;
@@ -379,24 +415,28 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   double *dX = nullptr, *dAlpha2 = nullptr, *dDiag = nullptr, *dY = nullptr, *dW = nullptr, *Lp = nullptr, *Xp = nullptr, *Tmp = nullptr,
          *dLin = nullptr;
   int* dFlag = nullptr;
-  struct Tmps { double** v[9]; int** f; ~Tmps() { for (auto q : v) if (q && *q) cudaFree(*q); if (f && *f) cudaFree(*f); } }
-      tmps{{&dX, &dAlpha2, &dDiag, &dY, &dW, &Lp, &Xp, &Tmp, &dLin}, &dFlag};
-
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->Us, (size_t)p * dp * Ns * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->scale, (size_t)p * dp * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->As, (size_t)p * Ns * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->LinvT, (size_t)p * T * KC * TILE_N * TILE_K * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->L, (size_t)p * N * N * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->Linv, (size_t)p * N * N * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&gp->a, (size_t)p * N * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dX, (size_t)d * N * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dAlpha2, p * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dDiag, p * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dY, (size_t)p * N * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dW, (size_t)p * N * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&Lp, pp * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&Xp, pp * 8));
-  BOSIP_CUDA(ctx, cudaMalloc(&dFlag, sizeof(int)));
+  {
+    // what the conditioned GP keeps: ONE allocation (cudaMalloc / cudaFree of these ~1.6 GB at N = 4096, p = 4 cost milliseconds each)
+    size_t off = 0;
+    auto carve = [&](size_t n_doubles) { size_t o = off; off += (n_doubles * 8 + 255) / 256 * 256; return o; };
+    const size_t o_Us = carve((size_t)p * dp * Ns), o_scale = carve((size_t)p * dp), o_As = carve((size_t)p * Ns),
+                 o_LinvT = carve((size_t)p * T * KC * TILE_N * TILE_K), o_L = carve((size_t)p * N * N), o_Linv = carve((size_t)p * N * N),
+                 o_a = carve((size_t)p * N);
+    BOSIP_CUDA(ctx, cudaMalloc(&gp->block, off));
+    char* base = reinterpret_cast<char*>(gp->block);
+    auto G = [&](size_t o) { return reinterpret_cast<double*>(base + o); };
+    gp->Us = G(o_Us); gp->scale = G(o_scale); gp->As = G(o_As); gp->LinvT = G(o_LinvT); gp->L = G(o_L); gp->Linv = G(o_Linv); gp->a = G(o_a);
+    // temporaries of the factorisation: the context's grow-only workspace (no allocation after the first fit of a size)
+    off = 0;
+    const size_t w_X = carve((size_t)d * N), w_alpha = carve(p), w_diag = carve(p), w_Y = carve((size_t)p * N), w_W = carve((size_t)p * P2),
+                 w_Lp = carve(pp), w_Xp = carve(pp), w_Tmp = carve((size_t)p * ((size_t)P2 * P2 / 2 + (size_t)64 * P2)),
+                 w_Lin = L_host ? carve((size_t)p * N * N) : 0, w_flag = carve(1);
+    BOSIP_TRY(ensure_ws(ctx, off));
+    auto Wp = [&](size_t o) { return reinterpret_cast<double*>(ctx->ws + o); };
+    dX = Wp(w_X); dAlpha2 = Wp(w_alpha); dDiag = Wp(w_diag); dY = Wp(w_Y); dW = Wp(w_W); Lp = Wp(w_Lp); Xp = Wp(w_Xp); Tmp = Wp(w_Tmp);
+    if (L_host) dLin = Wp(w_Lin);
+    dFlag = reinterpret_cast<int*>(ctx->ws + w_flag);
+  }
   BOSIP_CUDA(ctx, cudaMemsetAsync(Xp, 0, pp * 8, st));
   BOSIP_CUDA(ctx, cudaMemsetAsync(dFlag, 0, sizeof(int), st));
   BOSIP_CUDA(ctx, cudaMemcpyAsync(dX, X, (size_t)d * N * 8, cudaMemcpyHostToDevice, st));
@@ -404,6 +444,7 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   BOSIP_CUDA(ctx, cudaMemcpyAsync(dAlpha2, h_alpha2.data(), p * 8, cudaMemcpyHostToDevice, st));
   BOSIP_CUDA(ctx, cudaMemcpyAsync(dDiag, h_diag.data(), p * 8, cudaMemcpyHostToDevice, st));
 
+  mark("alloc+upload");
   scale_inputs_kernel<<<dim3((Ns + 127) / 128, dp, p), 128, 0, st>>>(dX, gp->scale, d, dp, N, Ns, gp->Us);
   BOSIP_CUDA(ctx, cudaGetLastError());
 
@@ -418,37 +459,57 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     BOSIP_CUDA(ctx, cudaMemcpyAsync(dY, h_resid.data(), h_resid.size() * 8, cudaMemcpyHostToDevice, st));
     build_K_kernel<<<dim3((P2 + 127) / 128, P2, p), 128, 0, st>>>(kernel_id, gp->Us, dp, N, Ns, P2, dAlpha2, dDiag, Lp);
     BOSIP_CUDA(ctx, cudaGetLastError());
-    // ---- blocked right-looking Cholesky
-    for (int b = 0; b < nb; ++b) {
-      potrf_diag_kernel<<<p, NB, POTRF_SMEM, st>>>(Lp, Xp, P2, b, 1, dFlag);
-      BOSIP_CUDA(ctx, cudaGetLastError());
-      const int rem = (nb - b - 1) * NB;
-      if (rem == 0) break;
-      const long long r0 = (long long)(b + 1) * NB, c0 = (long long)b * NB;
-      GemmArgs g{};
-      // panel: L21 = A21 * inv(L11)^T       (in place; a CTA reads its whole 64x64 A block before writing it)
-      g.A = Lp + r0 + c0 * P2; g.sam = 1; g.sak = P2;
-      g.B = Xp + c0 + c0 * P2; g.sbk = P2; g.sbn = 1;   // B(k,n) = Dinv(n,k)
-      g.C = Lp + r0 + c0 * P2; g.scm = 1; g.scn = P2;
-      g.bA1 = g.bB1 = g.bC1 = (long long)P2 * P2; g.nb1 = p; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0;
-      BOSIP_TRY(gemm64(ctx, g, rem, NB, p, st));
-      // trailing: A22 -= L21 L21^T  (lower tiles only)
-      g.A = Lp + r0 + c0 * P2; g.sam = 1; g.sak = P2;
-      g.B = Lp + r0 + c0 * P2; g.sbk = P2; g.sbn = 1;   // B(k,n) = L21(n,k)
-      g.C = Lp + r0 + r0 * P2; g.scm = 1; g.scn = P2;
-      g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1;
-      BOSIP_TRY(gemm64(ctx, g, rem, rem, p, st));
+    mark("build_K");
+    // ---- blocked right-looking Cholesky, two levels: inside a 256-column panel the 64-column sub-panels update only the rest of
+    //      that panel (K = 64); the big trailing update then runs ONCE per panel with K = 256, which quarters the read-modify-write
+    //      traffic on the trailing matrix (the part that does not fit the L2) and gives the GEMM 16 k-slabs per tile instead of 4
+    const int PANEL = 4 * NB;
+    for (int J = 0; J < P2; J += PANEL) {
+      const int Jw = std::min(PANEL, P2 - J);
+      for (int c0i = J; c0i < J + Jw; c0i += NB) {
+        potrf_diag_kernel<<<p, 256, POTRF_SMEM, st>>>(Lp, Xp, P2, c0i / NB, 1, dFlag);
+        BOSIP_CUDA(ctx, cudaGetLastError());
+        const int rem = P2 - (c0i + NB);
+        if (rem == 0) break;
+        const long long r0 = c0i + NB, c0 = c0i;
+        GemmArgs g{};
+        // panel: L21 = A21 * inv(L11)^T       (in place; a CTA has all of its A rows in shared memory before it writes them)
+        g.A = Lp + r0 + c0 * P2; g.sam = 1; g.sak = P2;
+        g.B = Xp + c0 + c0 * P2; g.sbk = P2; g.sbn = 1;   // B(k,n) = Dinv(n,k)
+        g.C = Lp + r0 + c0 * P2; g.scm = 1; g.scn = P2;
+        g.bA1 = g.bB1 = g.bC1 = (long long)P2 * P2; g.nb1 = p; g.K = NB; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0;
+        BOSIP_TRY(gemm64(ctx, g, rem, NB, p, st));
+        // inside the panel: A[r0:, r0:J+Jw] -= L21 L21^T  (lower tiles only)
+        const int n_in = (int)(J + Jw - r0);
+        if (n_in > 0) {
+          g.A = Lp + r0 + c0 * P2; g.sam = 1; g.sak = P2;
+          g.B = Lp + r0 + c0 * P2; g.sbk = P2; g.sbn = 1;   // B(k,n) = L21(n,k)
+          g.C = Lp + r0 + r0 * P2; g.scm = 1; g.scn = P2;
+          g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1;
+          BOSIP_TRY(gemm64(ctx, g, rem, n_in, p, st));
+        }
+      }
+      const long long rt = J + Jw;
+      const int remt = (int)(P2 - rt);
+      if (remt > 0) {   // trailing: A[rt:, rt:] -= L[rt:, J:rt] L[rt:, J:rt]^T
+        GemmArgs g{};
+        g.A = Lp + rt + (long long)J * P2; g.sam = 1; g.sak = P2;
+        g.B = Lp + rt + (long long)J * P2; g.sbk = P2; g.sbn = 1;
+        g.C = Lp + rt + rt * P2; g.scm = 1; g.scn = P2;
+        g.bA1 = g.bB1 = g.bC1 = (long long)P2 * P2; g.nb1 = p; g.K = Jw; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1;
+        BOSIP_TRY(gemm64(ctx, g, remt, remt, p, st));
+      }
     }
   } else {
-    BOSIP_CUDA(ctx, cudaMalloc(&dLin, (size_t)p * N * N * 8));
     BOSIP_CUDA(ctx, cudaMemcpyAsync(dLin, L_host, (size_t)p * N * N * 8, cudaMemcpyHostToDevice, st));
     pad_L_kernel<<<dim3((P2 + 127) / 128, P2, p), 128, 0, st>>>(dLin, N, P2, Lp);
     BOSIP_CUDA(ctx, cudaGetLastError());
     for (int b = 0; b < nb; ++b) {
-      potrf_diag_kernel<<<p, NB, POTRF_SMEM, st>>>(Lp, Xp, P2, b, 0, dFlag);
+      potrf_diag_kernel<<<p, 256, POTRF_SMEM, st>>>(Lp, Xp, P2, b, 0, dFlag);
       BOSIP_CUDA(ctx, cudaGetLastError());
     }
   }
+  mark("cholesky");
   int h_flag = 0;
   BOSIP_CUDA(ctx, cudaMemcpyAsync(&h_flag, dFlag, sizeof(int), cudaMemcpyDeviceToHost, st));
   BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
@@ -459,7 +520,6 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   // ---- triangular inverse by recursive doubling: X21 = -X22 (L21 X11).  Level s pairs block [2is, 2is+s) with
   //      [2is+s, 2is+2s); when P2 is not a multiple of 2s the last pair's second block is shorter (m rows) -- one more launch.
   if (nb > 1) {
-    BOSIP_CUDA(ctx, cudaMalloc(&Tmp, (size_t)p * ((size_t)P2 * P2 / 2 + (size_t)64 * P2) * 8));
     for (int s = NB; s < P2; s <<= 1) {
       const int npairs = P2 / (2 * s);
       const long long pair_stride = (long long)2 * s * (P2 + 1);
@@ -499,18 +559,22 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     }
   }
 
-  // ---- weights a = K^{-1} y: forward + backward substitution with L (trsv_chol_kernel)
+  mark("inverse");
+  // ---- weights a = K^{-1} y: forward + backward substitution with L, one launch per 64-row block and direction
   if (!L_host) {
-    const size_t trsv_smem = ((size_t)P2 + 4 * 64 + 64 + 64 * 65) * sizeof(double);
-    if (trsv_smem > 220 * 1024) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "N too large for the in-shared-memory triangular solve (N <= 23000)");
-    BOSIP_CUDA(ctx, cudaFuncSetAttribute(trsv_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsv_smem));
-    trsv_chol_kernel<<<p, 256, trsv_smem, st>>>(Lp, P2, N, dY, dW, gp->a);
+    pad_rhs_kernel<<<dim3((P2 + 255) / 256, p), 256, 0, st>>>(dY, N, P2, dW);
+    for (int b = 0; b < nb; ++b)
+      trsv_fwd_step<<<dim3(1 + (P2 - (b + 1) * NB + 255) / 256, p), 256, 0, st>>>(Lp, P2, b, dW);
+    for (int b = nb - 1; b >= 0; --b)
+      trsv_bwd_step<<<dim3(1 + (b * NB + 63) / 64, p), 256, 0, st>>>(Lp, P2, b, dW);
+    unpad_rhs_kernel<<<dim3((N + 255) / 256, p), 256, 0, st>>>(dW, N, P2, gp->a);
     BOSIP_CUDA(ctx, cudaGetLastError());
   } else {
     // a_host is N x p column-major == [p][N]
     BOSIP_CUDA(ctx, cudaMemcpyAsync(gp->a, a_host, (size_t)p * N * 8, cudaMemcpyHostToDevice, st));
   }
 
+  mark("solves");
   // ---- pack for the evaluator, keep plain copies for gp_get_factors
   {
     const size_t per_out = (size_t)T * KC * TILE_N * TILE_K;
@@ -521,6 +585,13 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     BOSIP_CUDA(ctx, cudaGetLastError());
   }
   BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
+  mark("pack");
+  if (trace) {
+    double prev = t_begin;
+    fprintf(stderr, "[fit trace N=%d p=%d P=%d]", N, p, P2);
+    for (auto& m : marks) { fprintf(stderr, " %s %.2f ms |", m.first, m.second - prev); prev = m.second; }
+    fprintf(stderr, " (frees follow)\n");
+  }
   guard.ok = true;
   *out = gp;
   return 0;

@@ -96,6 +96,18 @@ function _prior_desc(prior::Product)   # Product of Uniform / Normal / truncated
     return kinds, prm
 end
 
+# Likelihood descriptors of the closed-form Gaussian family (include/bosip_b200.h, BOSIP_B200_LIKE_*): (kind, z, so, sum_lengths).
+# The returned arrays must stay alive (GC.@preserve) while the struct built from their pointers is in use.
+_like_desc(l::NormalLikelihood)     = (Int32(0), Vector{Float64}(l.z_obs), Vector{Float64}(l.std_obs), Int32[])       # src/likelihoods/normal.jl:16-19
+_like_desc(l::LogNormalLikelihood)  = (Int32(1), Vector{Float64}(l.log_z_obs), Vector{Float64}(l.CV), Int32[])         # src/likelihoods/lognormal.jl:26-42
+_like_desc(l::NormalDiffLikelihood) = (Int32(2), Float64[], Vector{Float64}(l.std_obs), Int32[])                       # src/likelihoods/normal_diff.jl:17-19
+_like_desc(l::NormalSumLikelihood)  = (Int32(3), Vector{Float64}(l.z_obs), Vector{Float64}(l.std_obs), Vector{Int32}(l.sum_lengths))  # normal_sum.jl:18-27
+_like_desc(l::ExpLikelihood)        = (Int32(4), Float64[], Float64[], Int32[])                                         # src/likelihoods/exp.jl:7
+const B200Likelihood = Union{NormalLikelihood, LogNormalLikelihood, NormalDiffLikelihood, NormalSumLikelihood, ExpLikelihood}
+_obs_dim(kind, z, so, sl) = kind == 4 ? 1 : length(so)
+_like_struct(kind, z, so, sl) = LikeNormal(_obs_dim(kind, z, so, sl), kind, isempty(z) ? C_NULL : pointer(z), isempty(so) ? C_NULL : pointer(so),
+                                           isempty(sl) ? C_NULL : pointer(sl))
+
 function _posterior_eval(post::B200GPPosterior, like::NormalLikelihood, x_prior, X::AbstractMatrix{<:Real}, want::Cuint)
     Xc = Matrix{Float64}(X); M = size(Xc, 2)
     out = [((want & b) != 0) ? Vector{Float64}(undef, M) : C_NULL for b in (WANT_APPROX, WANT_MEAN, WANT_VAR)]
@@ -167,6 +179,220 @@ function calc_mmd_b200(kernel_id::Integer, lengthscales::Vector{Float64}, X::Mat
     ctx = context(); out = Ref{Cdouble}(0.0)
     check(ctx, ccall((:bosip_b200_mmd, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64, Cint, Ref{Cdouble}),
         ctx.h, kernel_id, size(X, 1), lengthscales, X, size(X, 2), Y, size(Y, 2), HOST, out))
+    return out[]
+end
+
+
+# ---- the other closed-form likelihoods (src/likelihoods/lognormal.jl:53-91, exp.jl:19-63, normal_sum.jl:68-115, normal_diff.jl:28-73),
+#      Bayesian-inference ensembles (src/posterior/log_posterior.jl:86-95,120-129,153-162) and evidence (src/posterior/evidence.jl:19-24)
+"One fused sweep for any closed-form likelihood and one or several conditioned GPs (`posts`: MultiFittedParams -> a vector)."
+function posterior_eval_b200(posts::Vector{<:B200GPPosterior}, like::B200Likelihood, x_prior, X::AbstractMatrix{<:Real}, want::Cuint;
+                             acq::Integer=-1, index_offset::Integer=0)
+    post = posts[1]; Xc = Matrix{Float64}(X); M = size(Xc, 2)
+    out = [((want & b) != 0) ? Vector{Float64}(undef, M) : C_NULL for b in (WANT_APPROX, WANT_MEAN, WANT_VAR)]
+    desc = isnothing(x_prior) ? (Int32[], Float64[]) : _prior_desc(x_prior)
+    lp = (isnothing(desc) && !isnothing(x_prior)) ? logpdf.(Ref(x_prior), eachcol(Xc)) : C_NULL
+    kinds, prm = isnothing(desc) ? (Int32[], Float64[]) : desc
+    kind, z, so, sl = _like_desc(like)
+    hs = Ptr{Cvoid}[q.h for q in posts]
+    ncl = Ref{Int64}(0); best_idx = Ref{Int64}(-1); best_val = Ref{Cdouble}(0.0)
+    GC.@preserve Xc out kinds prm lp z so sl hs posts begin
+        lk = Ref(_like_struct(kind, z, so, sl))
+        pr = Ref(Prior(post.d, isempty(kinds) ? C_NULL : pointer(kinds), isempty(prm) ? C_NULL : pointer(prm), lp === C_NULL ? C_NULL : pointer(lp)))
+        check(post.ctx, ccall((:bosip_b200_posterior_eval_bi, LIB), Cint,
+            (Ptr{Ptr{Cvoid}}, Cint, Ref{LikeNormal}, Ref{Prior}, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Cuint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+             Ref{Int64}, Cint, Int64, Ref{Int64}, Ref{Cdouble}),
+            hs, length(hs), lk, pr, Xc, M, HOST, C_NULL, want, out[1], out[2], out[3], ncl, acq, index_offset, best_idx, best_val))
+    end
+    return (log_approx_post=out[1], log_post_mean=out[2], log_post_var=out[3], n_clamped=ncl[], best_idx=best_idx[], best_val=best_val[])
+end
+posterior_eval_b200(post::B200GPPosterior, args...; kw...) = posterior_eval_b200([post], args...; kw...)
+
+# more specific methods for the remaining closed-form likelihoods and for MultiFittedParams (a vector of posteriors)
+for L in (:LogNormalLikelihood, :NormalDiffLikelihood, :NormalSumLikelihood, :ExpLikelihood)
+    @eval begin
+        BOSIP.log_approx_likelihood(like::$L, post::B200GPPosterior) = _closure_any([post], like, nothing, WANT_APPROX, :log_approx_post)
+        BOSIP.log_likelihood_mean(like::$L, post::B200GPPosterior) = _closure_any([post], like, nothing, WANT_MEAN, :log_post_mean)
+        BOSIP.log_likelihood_variance(like::$L, post::B200GPPosterior) = _closure_any([post], like, nothing, WANT_VAR, :log_post_var)
+    end
+end
+_closure_any(posts, like, prior, want, key) = (f(X::AbstractMatrix{<:Real}) = getfield(posterior_eval_b200(posts, like, prior, X, want), key);
+                                               f(x::AbstractVector{<:Real}) = f(reshape(x, :, 1))[1]; f)
+"BI variants of the posterior closures: `posts = BOSS.model_posterior(problem)` with MultiFittedParams (log_posterior.jl:86-95,120-129,153-162)."
+fused_log_approx_posterior(bosip::BosipProblem, posts::Vector{<:B200GPPosterior}) = _closure_any(posts, bosip.likelihood, bosip.x_prior, WANT_APPROX, :log_approx_post)
+fused_log_posterior_mean(bosip::BosipProblem, posts::Vector{<:B200GPPosterior}) = _closure_any(posts, bosip.likelihood, bosip.x_prior, WANT_MEAN, :log_post_mean)
+fused_log_posterior_variance(bosip::BosipProblem, posts::Vector{<:B200GPPosterior}) = _closure_any(posts, bosip.likelihood, bosip.x_prior, WANT_VAR, :log_post_var)
+
+"evidence(post, x_prior; xs) (src/posterior/evidence.jl:19-24) in one sweep; `which` = WANT_APPROX or WANT_MEAN; ensembles are averaged in linear space."
+function evidence_b200(posts::Vector{<:B200GPPosterior}, like::B200Likelihood, x_prior::Product, xs::AbstractMatrix{<:Real}; which::Cuint=WANT_MEAN)
+    post = posts[1]; Xc = Matrix{Float64}(xs); S = size(Xc, 2)
+    kinds, prm = _prior_desc(x_prior); kind, z, so, sl = _like_desc(like)
+    hs = Ptr{Cvoid}[q.h for q in posts]; out = Ref{Cdouble}(0.0)
+    GC.@preserve Xc kinds prm z so sl hs posts begin
+        check(post.ctx, ccall((:bosip_b200_evidence_sum_bi, LIB), Cint,
+            (Ptr{Ptr{Cvoid}}, Cint, Ref{LikeNormal}, Ref{Prior}, Ptr{Cdouble}, Int64, Cint, Cuint, Ref{Cdouble}),
+            hs, length(hs), Ref(_like_struct(kind, z, so, sl)), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)), Xc, S, HOST, which, out))
+    end
+    return out[] / S
+end
+
+"Candidate-set argmax for an ensemble (MultiFittedParams): bosip_b200_acq_argmax_bi."
+function acq_argmax_b200(posts::Vector{<:B200GPPosterior}, like::B200Likelihood, x_prior::Product, src::CandSrc, M::Integer, acq::Integer; keep=nothing)
+    post = posts[1]; kinds, prm = _prior_desc(x_prior); kind, z, so, sl = _like_desc(like)
+    hs = Ptr{Cvoid}[q.h for q in posts]
+    best_idx, best_val, best_x = Ref{Int64}(-1), Ref{Cdouble}(0.0), Vector{Float64}(undef, post.d)
+    GC.@preserve kinds prm z so sl hs posts keep best_x begin
+        check(post.ctx, ccall((:bosip_b200_acq_argmax_bi, LIB), Cint,
+            (Ptr{Ptr{Cvoid}}, Cint, Ref{LikeNormal}, Ref{Prior}, Ref{CandSrc}, Int64, Int64, Cint, Ref{Int64}, Ref{Cdouble}, Ptr{Cdouble}),
+            hs, length(hs), Ref(_like_struct(kind, z, so, sl)), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)), Ref(src), M, 0, acq,
+            best_idx, best_val, best_x))
+    end
+    return best_x, best_val[], best_idx[]
+end
+
+# ---- marginal-integration sweep: the body of `_compute_marginals_int` (ext/CairoExt.jl:146-246) in ONE ccall -------------------
+"""
+    diag, pairs = marginals_int_b200(post, like, x_prior, lhc, grid_size, lb, ub; which=WANT_MEAN)
+
+`lhc` is the d x G Latin-hypercube matrix `generate_LHC(bounds, lhc_grid_size)` (ext/CairoExt.jl:92).  Returns the UN-normalised means
+`diag[i, k]` (grid_size x d) and `pairs[ia, ib, pair]` (pairs ordered (1,2),(1,3),...,(d-1,d) as the reference's loops); apply
+`normalize_prob_vals!` (ext/CairoExt.jl:410-430) afterwards.
+"""
+function marginals_int_b200(post::B200GPPosterior, like::B200Likelihood, x_prior::Product, lhc::AbstractMatrix{<:Real}, grid_size::Integer,
+                            lb::Vector{Float64}, ub::Vector{Float64}; which::Cuint=WANT_MEAN)
+    d = post.d; G = size(lhc, 2); L = Matrix{Float64}(lhc)
+    diag = Matrix{Float64}(undef, grid_size, d); pairs = Array{Float64}(undef, grid_size, grid_size, d * (d - 1) ÷ 2)
+    kinds, prm = _prior_desc(x_prior); kind, z, so, sl = _like_desc(like)
+    GC.@preserve L diag pairs kinds prm z so sl lb ub begin
+        check(post.ctx, ccall((:bosip_b200_marginals_int, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LikeNormal}, Ref{Prior}, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cuint, Ptr{Cdouble}, Ptr{Cdouble}),
+            post.h, Ref(_like_struct(kind, z, so, sl)), Ref(Prior(d, pointer(kinds), pointer(prm), C_NULL)), L, G, grid_size, lb, ub, which,
+            diag, isempty(pairs) ? C_NULL : pairs))
+    end
+    return diag, pairs
+end
+
+# ---- confidence sets / AEConfidence (src/utils/confidence_set.jl:19-81, src/term_conds/ae_confidence.jl:59-79) ---------------------
+"quantile(vals, Distributions.weights(ws), p) on the device (what find_cutoff computes, confidence_set.jl:24-26)."
+function weighted_quantile_b200(vals::Vector{Float64}, ws::Vector{Float64}, p::Real)
+    ctx = context(); out = Ref{Cdouble}(0.0)
+    check(ctx, ccall((:bosip_b200_weighted_quantile, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Cint, Cdouble, Ref{Cdouble}),
+        ctx.h, vals, ws, length(vals), HOST, p, out))
+    return out[]
+end
+BOSIP.find_cutoff(vals::Vector{Float64}, ws::Vector{Float64}, q::Real, ::Val{:b200}) = weighted_quantile_b200(vals, ws, 1.0 - q)
+function approx_cutoff_area_b200(vals::Vector{Float64}, ws::Vector{Float64}, c::Real)          # confidence_set.jl:52-56
+    ctx = context(); out = Ref{Cdouble}(0.0)
+    check(ctx, ccall((:bosip_b200_cutoff_area, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Cint, Cdouble, Ref{Cdouble}),
+        ctx.h, vals, ws, length(vals), HOST, c, out))
+    return out[]
+end
+function set_iou_b200(in_A::AbstractVector{Bool}, in_B::AbstractVector{Bool}, xs_logpdf::Vector{Float64})   # confidence_set.jl:73-81
+    ctx = context(); out = Ref{Cdouble}(0.0); a = Vector{Bool}(in_A); b = Vector{Bool}(in_B)              # BitVector -> one byte per flag
+    check(ctx, ccall((:bosip_b200_set_iou, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt8}, Ptr{Cdouble}, Int64, Cint, Ref{Cdouble}),
+        ctx.h, a, b, xs_logpdf, length(a), HOST, out))
+    return out[]
+end
+"calculate(::AEConfidence, bosip) (ae_confidence.jl:59-79): ONE fused sweep for both closures + one device reduction."
+function BOSIP.calculate(cond::BOSIP.AEConfidence, bosip::BosipProblem, ::Val{:b200})
+    xs = isnothing(cond.xs) ? rand(bosip.x_prior, cond.samples) : cond.xs
+    post = BOSS.model_posterior(bosip.problem)
+    r = posterior_eval_b200(post isa Vector ? post : [post], bosip.likelihood, bosip.x_prior, xs, WANT_APPROX | WANT_MEAN)
+    xs_logpdf = logpdf.(Ref(bosip.x_prior), eachcol(xs))
+    ctx = context(); iou = Ref{Cdouble}(0.0); ca = Ref{Cdouble}(0.0); ce = Ref{Cdouble}(0.0)
+    check(ctx, ccall((:bosip_b200_confidence_iou, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Cint, Cdouble, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}),
+        ctx.h, r.log_approx_post, r.log_post_mean, xs_logpdf, length(xs_logpdf), HOST, cond.q, iou, ca, ce))
+    return iou[]
+end
+
+# ---- multi-GPU from ONE Julia process (csrc/multi.cu): bosip_b200_init_multi + the `_multi` entry points ----------------------------
+mutable struct MultiContext
+    h::Ptr{Cvoid}; ndev::Int
+    function MultiContext(devices::Vector{<:Integer})
+        h = Ref{Ptr{Cvoid}}(C_NULL); devs = Vector{Cint}(devices)
+        rc = ccall((:bosip_b200_init_multi, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), length(devs), devs, h)
+        rc == 0 || error(unsafe_string(ccall((:bosip_b200_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        m = new(h[], length(devs))
+        finalizer(c -> ccall((:bosip_b200_shutdown_multi, LIB), Cint, (Ptr{Cvoid},), c.h), m)
+    end
+end
+MultiContext(ndev::Integer) = MultiContext(collect(0:ndev-1))
+function check(m::MultiContext, rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:bosip_b200_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m.h))
+    rc == EDOMAIN && throw(DomainError(NaN, msg)); rc == ENOTPD && throw(LinearAlgebra.PosDefException(1))
+    error("bosip_b200 [$rc]: $msg")
+end
+mutable struct B200MultiGPPosterior{M} <: BOSS.ModelPosterior{M}
+    m::MultiContext; h::Ptr{Cvoid}; d::Int; p::Int
+end
+"Replicated fit on every device of `m` (the `_multi` counterpart of BOSS.model_posterior, src/posterior/log_posterior.jl:81)."
+function model_posterior_multi(m::MultiContext, model::B200GaussianProcess, params::BOSS.UniFittedParams, data::BOSS.ExperimentData)
+    X, Y = Matrix{Float64}(data.X), Matrix{Float64}(data.Y)
+    λ, α, σ = params.lengthscales, params.amplitude, params.noise_std
+    d, N = size(X); p = size(Y, 1)
+    h = Ref{Ptr{Cvoid}}(C_NULL); opts = Ref(GpOpts(0.0, 0, 1))
+    GC.@preserve X Y λ α σ begin
+        check(m, ccall((:bosip_b200_gp_fit_multi, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{GpOpts}, Ref{Ptr{Cvoid}}),
+            m.h, kernel_id(model.gp.kernel), d, N, p, X, Y, λ, α, σ, C_NULL, opts, h))
+    end
+    post = B200MultiGPPosterior{typeof(model)}(m, h[], d, p)
+    finalizer(q -> ccall((:bosip_b200_gp_free_multi, LIB), Cint, (Ptr{Cvoid},), q.h), post)
+end
+"Posterior closures' sweep over contiguous ranges of X on all devices; same outputs as `posterior_eval_b200`."
+function posterior_eval_multi(post::B200MultiGPPosterior, like::B200Likelihood, x_prior::Product, X::AbstractMatrix{<:Real}, want::Cuint;
+                              acq::Integer=-1, index_offset::Integer=0)
+    Xc = Matrix{Float64}(X); M = size(Xc, 2)
+    out = [((want & b) != 0) ? Vector{Float64}(undef, M) : C_NULL for b in (WANT_APPROX, WANT_MEAN, WANT_VAR)]
+    kinds, prm = _prior_desc(x_prior); kind, z, so, sl = _like_desc(like)
+    ncl = Ref{Int64}(0); best_idx = Ref{Int64}(-1); best_val = Ref{Cdouble}(0.0)
+    GC.@preserve Xc out kinds prm z so sl begin
+        check(post.m, ccall((:bosip_b200_posterior_eval_multi, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LikeNormal}, Ref{Prior}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Cuint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Int64},
+             Cint, Int64, Ref{Int64}, Ref{Cdouble}),
+            post.h, Ref(_like_struct(kind, z, so, sl)), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)), Xc, M, C_NULL, want,
+            out[1], out[2], out[3], ncl, acq, index_offset, best_idx, best_val))
+    end
+    return (log_approx_post=out[1], log_post_mean=out[2], log_post_var=out[3], n_clamped=ncl[], best_idx=best_idx[], best_val=best_val[])
+end
+"B200CandidateAM over all devices: the candidate range is sharded inside the library, the winners combined in rank order."
+function maximize_acquisition_multi(am::B200CandidateAM, post::B200MultiGPPosterior, like::B200Likelihood, x_prior::Product, lb::Vector{Float64},
+                                    ub::Vector{Float64}, acq::Integer)
+    kinds, prm = _prior_desc(x_prior); kind, z, so, sl = _like_desc(like)
+    best_idx, best_val, best_x = Ref{Int64}(-1), Ref{Cdouble}(0.0), Vector{Float64}(undef, post.d)
+    GC.@preserve am kinds prm z so sl lb ub best_x begin
+        src = isnothing(am.candidates) ? CandSrc(1, 0, C_NULL, am.seed, pointer(lb), pointer(ub), 0) :
+                                         CandSrc(0, 0, pointer(am.candidates), 0, C_NULL, C_NULL, 0)
+        M = isnothing(am.candidates) ? am.count : size(am.candidates, 2)
+        check(post.m, ccall((:bosip_b200_acq_argmax_multi, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LikeNormal}, Ref{Prior}, Ref{CandSrc}, Int64, Int64, Cint, Ref{Int64}, Ref{Cdouble}, Ptr{Cdouble}),
+            post.h, Ref(_like_struct(kind, z, so, sl)), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)), Ref(src), M, 0, acq,
+            best_idx, best_val, best_x))
+    end
+    return best_x, best_val[]
+end
+function evidence_multi(post::B200MultiGPPosterior, like::B200Likelihood, x_prior::Product, xs::AbstractMatrix{<:Real}; which::Cuint=WANT_MEAN)
+    Xc = Matrix{Float64}(xs); S = size(Xc, 2); out = Ref{Cdouble}(0.0)
+    kinds, prm = _prior_desc(x_prior); kind, z, so, sl = _like_desc(like)
+    GC.@preserve Xc kinds prm z so sl begin
+        check(post.m, ccall((:bosip_b200_evidence_sum_multi, LIB), Cint,
+            (Ptr{Cvoid}, Ref{LikeNormal}, Ref{Prior}, Ptr{Cdouble}, Int64, Cuint, Ref{Cdouble}),
+            post.h, Ref(_like_struct(kind, z, so, sl)), Ref(Prior(post.d, pointer(kinds), pointer(prm), C_NULL)), Xc, S, which, out))
+    end
+    return out[] / S
+end
+function calc_mmd_multi(m::MultiContext, kernel_id::Integer, lengthscales::Vector{Float64}, X::Matrix{Float64}, Y::Matrix{Float64})
+    out = Ref{Cdouble}(0.0)
+    check(m, ccall((:bosip_b200_mmd_multi, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64, Ref{Cdouble}),
+        m.h, kernel_id, size(X, 1), lengthscales, X, size(X, 2), Y, size(Y, 2), out))
+    return out[]
+end
+function calc_tv_multi(m::MultiContext, log_ws::Vector{Float64}, approx_logvals::Vector{Float64}, true_logvals::Vector{Float64})
+    out = Ref{Cdouble}(0.0)
+    check(m, ccall((:bosip_b200_tv_multi, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ref{Cdouble}),
+        m.h, log_ws, approx_logvals, true_logvals, length(log_ws), out))
     return out[]
 end
 

@@ -374,12 +374,16 @@ def posterior_eval(fit: GPFit, like: NormalLikelihood, prior: ProductPrior, Xq, 
     mu, var = gp_predict(fit, Xq, mean_at_Xq, True, gemm_trick)
     std = np.sqrt(var)
     lp = log_prior(prior, Xq)
-    return {
+    out = {
         "mu": mu, "var": var, "log_prior": lp,
         "log_approx_post": lp + loglike(like, mu),
         "log_post_mean": lp + log_likelihood_mean(like, mu, std),
         "log_post_var": 2.0 * lp + log_likelihood_variance(like, mu, std),
     }
+    if isinstance(like, NormalLikelihood):   # the two terms of V = exp(log E[l^2]) - exp(2 log E[l]): the tests bound the cancellation with them
+        out["log_like_mean"] = log_likelihood_mean(like, mu, std)
+        out["log_sq_like_mean"] = log_sq_likelihood_mean(like, mu, std)
+    return out
 
 
 def posterior_eval_bi(fits: Sequence[GPFit], like: NormalLikelihood, prior: ProductPrior, Xq):

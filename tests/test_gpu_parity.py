@@ -38,8 +38,15 @@ def assert_mu(mu, omu):
 
 
 def assert_var(var, ovar, kxx):
-    # 1e-10 relative where the variance is not dominated by the cancellation alpha^2 - ||v||^2
-    assert np.max(np.abs(var - ovar) / (np.abs(ovar) + 1e-3 * kxx[:, None])) < TOL
+    # 1e-10 RELATIVE wherever sigma^2 / k(x,x) >= 1e-6.  Below that the subtraction alpha^2 - ||v||^2 has
+    # cancelled six digits and both sides carry kappa(L) * eps of it: the bound there is absolute, 1e-10 of the 1e-6 k(x,x) floor
+    # times the 1e3 the old gate allowed (never reached by these problems: their smallest variance is ~6e-4 k(x,x), on top of the
+    # training points).  Observed with queries ON training points (tools/gate_probe.py, profiles/r02_gate_probe.jsonl):
+    # <= 1.5e-11 relative on either engine.
+    k = kxx[:, None] * np.ones_like(ovar)
+    big = ovar >= 1e-6 * k
+    assert np.max((np.abs(var - ovar) / np.maximum(np.abs(ovar), 1e-300))[big], initial=0.0) < TOL
+    assert np.max((np.abs(var - ovar) / k)[~big], initial=0.0) < 1e-13
 
 
 def assert_logs(res, ores):
@@ -67,7 +74,7 @@ def test_fit_predict_and_closures_vs_oracle(bb, ctx, name, M):
     post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)
     Lg, Lig, ag = post.factors()
     assert np.max(np.abs(Lg - ofit.L)) / np.max(np.abs(ofit.L)) < 1e-12
-    assert np.max(np.abs(ag - ofit.a)) / np.max(np.abs(ofit.a)) < 1e-9   # kappa(K) * eps
+    assert np.max(np.abs(ag - ofit.a)) / np.max(np.abs(ofit.a)) < 1e-11  # two triangular solves with L (observed <= 3e-13); was 1e-9 through L^-1
     for j in range(pr.p):
         assert np.max(np.abs(Lig[j] @ ofit.L[j] - np.eye(pr.N))) < 1e-11
     omu, ovar = orc.gp_predict(ofit, Xq)

@@ -181,7 +181,7 @@ def test_julia_glue_matches_header():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     h = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "bosip_b200.h")).read(), flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(?:int|const char\s*\*)\s+(bosip_b200_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+    for m in re.finditer(r"\b(?:int|const char\s*\*|bosip_b200_ctx\s*\*|bosip_b200_gp\s*\*)\s+(bosip_b200_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
         protos[m.group(1)] = [a for a in m.group(2).replace("\n", " ").split(",") if a.strip() and a.strip() != "void"]
     seen = 0
     for rel in (os.path.join("julia", "BosipB200.jl"), "INTEGRATION.md"):
