@@ -194,7 +194,7 @@ __global__ void pad_L_kernel(const double* __restrict__ Lin, int N, int P2, doub
 // same block of Xp.  One CTA of 256 threads per output; both halves are right-looking rank-1 sweeps over shared memory with the
 // trailing region spread over all threads (two barriers per column).  flag[0] = 1 + block index on a non-positive pivot.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap, double* __restrict__ Xp, int P2, int b,
-                                                         int do_factor, int* __restrict__ flag) {
+                                                         int do_factor, int* __restrict__ flag, const double* __restrict__ piv_floor) {
   extern __shared__ __align__(16) unsigned char potrf_smem[];
   double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
   double (*x)[NB + 1] = s + NB;
@@ -205,12 +205,26 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap
   __syncthreads();
   if (do_factor) {
     bool ok = true;
+    // "not positive definite" = a pivot at or below rounding level of the original diagonal K_cc = alpha^2 + sigma^2 + jitter
+    // (LAPACK / Julia's cholesky test `<= 0`, which for an exactly singular K is decided by rounding noise; the floor makes the
+    // PosDefException deterministic and never fires for a noise variance above 1e-14 of the prior variance)
+    const double floor_j = piv_floor ? piv_floor[j] : 0.0;
     for (int c = 0; c < NB; ++c) {
       const double piv = s[c][c];
-      if (!(piv > 0.0)) { if (tid == 0) atomicCAS(flag, 0, 1 + b); ok = false; break; }  // uniform: every thread reads the same pivot
-      const double lcc = sqrt(piv);
+      if (!(piv > floor_j)) { if (tid == 0) atomicCAS(flag, 0, 1 + b); ok = false; break; }  // uniform: every thread reads the same pivot
+      // sqrt and reciprocal from ONE Goldschmidt iteration (hardware rsqrt seed, two coupled steps, residual correction: <= 2 ulp,
+      // fastmath.cuh) instead of the library's sqrt + divide, which put ~800 dependent cycles into each of the 64 serial steps
+      double yv;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yv) : "d"(piv));
+      double gg = piv * yv, hh = 0.5 * yv;
+      double rr_ = fma(-hh, gg, 0.5);
+      gg = fma(gg, rr_, gg); hh = fma(hh, rr_, hh);
+      rr_ = fma(-hh, gg, 0.5);
+      gg = fma(gg, rr_, gg); hh = fma(hh, rr_, hh);
+      const double lcc = fma(fma(-gg, gg, piv), hh, gg);          // sqrt(piv)
+      const double rinv = 2.0 * fma(hh, fma(-2.0 * hh, lcc, 1.0), hh);   // 1 / lcc: one Newton step on 2 h
       if (tid == c) diag[c] = lcc;
-      if (tq == 0 && tr > c) s[tr][c] = s[tr][c] / lcc;            // column c of L (the pivot itself stays in place until the write-back)
+      if (tq == 0 && tr > c) s[tr][c] = s[tr][c] * rinv;            // column c of L (the pivot itself stays in place until the write-back)
       __syncthreads();
       // rank-1 update of the trailing lower triangle: row tr, columns c+1+tq, c+5+tq, ... <= tr
       if (tr > c) {
@@ -232,10 +246,11 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap
   // inverse: solve L X = I column-block-wise as 64 rank-1 sweeps: X[k][:] = B[k][:] / L[k][k], then B[i][:] -= L[i][k] X[k][:]
   // for the rows below (only columns <= k of row k are non-zero)
   for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; x[rr][cc] = rr == cc ? 1.0 : 0.0; }
+  if (tid < NB) diag[tid] = 1.0 / s[tid][tid];     // the 64 reciprocals at once (exact divisions, off the serial path)
   __syncthreads();
   for (int k = 0; k < NB; ++k) {
-    const double dkk = s[k][k];
-    if (tq == 0 && tr <= k) x[k][tr] = x[k][tr] / dkk;
+    const double rk = diag[k];
+    if (tq == 0 && tr <= k) x[k][tr] = x[k][tr] * rk;
     __syncthreads();
     // rows i = k+1 .. 63 (index tr), columns jj = tq, tq+4, ... <= k
     if (tr > k) {
@@ -250,7 +265,8 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap
 
 // a = K^{-1} y = L^{-T} (L^{-1} y) by two blocked triangular SOLVES with the Cholesky factor itself (not through the explicit
 // inverse).  One launch per 64-row block and direction, all outputs batched: every CTA substitutes the 64 x 64 diagonal system
-// exactly (warp 0: two rows per lane, the pivot row's value broadcast by shuffle, true divisions -- redundant across CTAs, which
+// exactly (warp 0: two rows per lane, the pivot row's value broadcast by shuffle, multiplied by the reciprocal diagonal, which is
+// formed once per block by 64 parallel divisions -- redundant across CTAs, which
 // costs nothing but keeps the step to ONE kernel), CTA 0 stores the block's solution, CTA c >= 1 applies the block's solution
 // to its share of the remaining right-hand side (a GEMV slab with coalesced reads).  rhs is [p][P], zero padded.
 __device__ __forceinline__ void trsv_load_block(const double* __restrict__ L, int P, int r0, double (*D)[65]) {
@@ -262,13 +278,16 @@ __global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ 
   const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r0 = b * 64;
   const double* L = Lp + (size_t)j * P * P;
   double* y = rhs + (size_t)j * P;
+  __shared__ double rd[64];
   trsv_load_block(L, P, r0, D);
+  __syncthreads();
+  if (tid < 64) rd[tid] = 1.0 / D[tid][tid];   // the 64 reciprocals at once: no division on the 64-step serial path
   __syncthreads();
   if (warp == 0) {
     double x0 = y[r0 + lane], x1 = y[r0 + lane + 32];
     for (int k = 0; k < 64; ++k) {
       const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
-      const double wk = rk / D[k][k];
+      const double wk = rk * rd[k];
       if (lane == (k & 31)) { if (k < 32) x0 = wk; else x1 = wk; }
       if (lane > k) x0 = fma(-D[lane][k], wk, x0);
       if (lane + 32 > k) x1 = fma(-D[lane + 32][k], wk, x1);
@@ -291,13 +310,16 @@ __global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ 
   const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r0 = b * 64;
   const double* L = Lp + (size_t)j * P * P;
   double* w = rhs + (size_t)j * P;
+  __shared__ double rd[64];
   trsv_load_block(L, P, r0, D);
+  __syncthreads();
+  if (tid < 64) rd[tid] = 1.0 / D[tid][tid];
   __syncthreads();
   if (warp == 0) {
     double x0 = w[r0 + lane], x1 = w[r0 + lane + 32];
     for (int k = 63; k >= 0; --k) {
       const double rk = __shfl_sync(0xffffffffu, k < 32 ? x0 : x1, k & 31);
-      const double ak = rk / D[k][k];
+      const double ak = rk * rd[k];
       if (lane == (k & 31)) { if (k < 32) x0 = ak; else x1 = ak; }
       if (lane < k) x0 = fma(-D[k][lane], ak, x0);          // column `lane` of row k of L^T = L[k][lane]
       if (lane + 32 < k) x1 = fma(-D[k][lane + 32], ak, x1);
@@ -397,22 +419,23 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   bosip_b200_gp_opts dflt = {0.0, 0, 1};
   gp->opts = opts_in ? *opts_in : dflt;
   const int dp = gp->dp, Ns = gp->Ns, T = gp->T, KC = gp->KC, P2 = padded_size(N);
-  cudaStream_t st = ctx->s_comp;
+  cudaStream_t st = ctx->s_comp, sb = ctx->s_in, ss = ctx->s_out;   // main | trailing-update lookahead | triangular solves
   struct Guard { Gp* g; bool ok = false; ~Guard() { if (!ok) gp_destroy(g); } } guard{gp};
 
   // ---- small host-side parameter prep
   const double ck = kernel_id == BOSIP_B200_KERNEL_SE ? sqrt(0.5) : kernel_id == BOSIP_B200_KERNEL_MATERN32 ? sqrt(3.0) : sqrt(5.0);
-  std::vector<double> h_scale((size_t)p * dp, 0.0), h_alpha2(p), h_diag(p), h_resid;
+  std::vector<double> h_scale((size_t)p * dp, 0.0), h_alpha2(p), h_diag(p), h_floor(p), h_resid;
   for (int j = 0; j < p; ++j) {
     for (int k = 0; k < d; ++k) h_scale[(size_t)j * dp + k] = ck / lambda[k + d * j];
     h_alpha2[j] = alpha[j] * alpha[j];
     gp->alpha2[j] = h_alpha2[j];
     gp->sig2[j] = sigma[j] * sigma[j];
     h_diag[j] = sigma[j] * sigma[j] + gp->opts.jitter;
+    h_floor[j] = 1e-14 * (h_alpha2[j] + h_diag[j]);
   }
 
   const size_t pp = (size_t)p * P2 * P2;
-  double *dX = nullptr, *dAlpha2 = nullptr, *dDiag = nullptr, *dY = nullptr, *dW = nullptr, *Lp = nullptr, *Xp = nullptr, *Tmp = nullptr,
+  double *dX = nullptr, *dAlpha2 = nullptr, *dDiag = nullptr, *dFloor = nullptr, *dY = nullptr, *dW = nullptr, *Lp = nullptr, *Xp = nullptr, *Tmp = nullptr,
          *dLin = nullptr;
   int* dFlag = nullptr;
   {
@@ -428,12 +451,12 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     gp->Us = G(o_Us); gp->scale = G(o_scale); gp->As = G(o_As); gp->LinvT = G(o_LinvT); gp->L = G(o_L); gp->Linv = G(o_Linv); gp->a = G(o_a);
     // temporaries of the factorisation: the context's grow-only workspace (no allocation after the first fit of a size)
     off = 0;
-    const size_t w_X = carve((size_t)d * N), w_alpha = carve(p), w_diag = carve(p), w_Y = carve((size_t)p * N), w_W = carve((size_t)p * P2),
+    const size_t w_X = carve((size_t)d * N), w_alpha = carve(p), w_diag = carve(p), w_floor = carve(p), w_Y = carve((size_t)p * N), w_W = carve((size_t)p * P2),
                  w_Lp = carve(pp), w_Xp = carve(pp), w_Tmp = carve((size_t)p * ((size_t)P2 * P2 / 2 + (size_t)64 * P2)),
                  w_Lin = L_host ? carve((size_t)p * N * N) : 0, w_flag = carve(1);
     BOSIP_TRY(ensure_ws(ctx, off));
     auto Wp = [&](size_t o) { return reinterpret_cast<double*>(ctx->ws + o); };
-    dX = Wp(w_X); dAlpha2 = Wp(w_alpha); dDiag = Wp(w_diag); dY = Wp(w_Y); dW = Wp(w_W); Lp = Wp(w_Lp); Xp = Wp(w_Xp); Tmp = Wp(w_Tmp);
+    dX = Wp(w_X); dAlpha2 = Wp(w_alpha); dDiag = Wp(w_diag); dFloor = Wp(w_floor); dY = Wp(w_Y); dW = Wp(w_W); Lp = Wp(w_Lp); Xp = Wp(w_Xp); Tmp = Wp(w_Tmp);
     if (L_host) dLin = Wp(w_Lin);
     dFlag = reinterpret_cast<int*>(ctx->ws + w_flag);
   }
@@ -443,6 +466,7 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   BOSIP_CUDA(ctx, cudaMemcpyAsync(gp->scale, h_scale.data(), h_scale.size() * 8, cudaMemcpyHostToDevice, st));
   BOSIP_CUDA(ctx, cudaMemcpyAsync(dAlpha2, h_alpha2.data(), p * 8, cudaMemcpyHostToDevice, st));
   BOSIP_CUDA(ctx, cudaMemcpyAsync(dDiag, h_diag.data(), p * 8, cudaMemcpyHostToDevice, st));
+  BOSIP_CUDA(ctx, cudaMemcpyAsync(dFloor, h_floor.data(), p * 8, cudaMemcpyHostToDevice, st));
 
   mark("alloc+upload");
   scale_inputs_kernel<<<dim3((Ns + 127) / 128, dp, p), 128, 0, st>>>(dX, gp->scale, d, dp, N, Ns, gp->Us);
@@ -464,10 +488,11 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     //      that panel (K = 64); the big trailing update then runs ONCE per panel with K = 256, which quarters the read-modify-write
     //      traffic on the trailing matrix (the part that does not fit the L2) and gives the GEMM 16 k-slabs per tile instead of 4
     const int PANEL = 4 * NB;
+    bool big_pending = false;
     for (int J = 0; J < P2; J += PANEL) {
       const int Jw = std::min(PANEL, P2 - J);
       for (int c0i = J; c0i < J + Jw; c0i += NB) {
-        potrf_diag_kernel<<<p, 256, POTRF_SMEM, st>>>(Lp, Xp, P2, c0i / NB, 1, dFlag);
+        potrf_diag_kernel<<<p, 256, POTRF_SMEM, st>>>(Lp, Xp, P2, c0i / NB, 1, dFlag, dFloor);
         BOSIP_CUDA(ctx, cudaGetLastError());
         const int rem = P2 - (c0i + NB);
         if (rem == 0) break;
@@ -491,21 +516,36 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
       }
       const long long rt = J + Jw;
       const int remt = (int)(P2 - rt);
-      if (remt > 0) {   // trailing: A[rt:, rt:] -= L[rt:, J:rt] L[rt:, J:rt]^T
+      if (remt > 0) {   // trailing: A[rt:, rt:] -= L[rt:, J:rt] L[rt:, J:rt]^T, with LOOKAHEAD:
+        // (i) the next panel's columns [rt, rt + 256) on the main stream -- the sub-panel chain of the next panel (64 latency-bound
+        // launches of ~100 us with a handful of CTAs each) depends on nothing else; (ii) the rest of the trailing matrix on a side
+        // stream, where its big GEMM overlaps that chain.  (i) and the next (ii) read-modify-write what the previous (ii) wrote.
         GemmArgs g{};
-        g.A = Lp + rt + (long long)J * P2; g.sam = 1; g.sak = P2;
-        g.B = Lp + rt + (long long)J * P2; g.sbk = P2; g.sbn = 1;
-        g.C = Lp + rt + rt * P2; g.scm = 1; g.scn = P2;
+        g.sam = 1; g.sak = P2; g.sbk = P2; g.sbn = 1; g.scm = 1; g.scn = P2;
         g.bA1 = g.bB1 = g.bC1 = (long long)P2 * P2; g.nb1 = p; g.K = Jw; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1;
-        BOSIP_TRY(gemm64(ctx, g, remt, remt, p, st));
+        const int n_i = std::min(PANEL, remt);
+        if (big_pending) BOSIP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_comp[1], 0));   // the previous panel's (ii) has finished
+        g.A = Lp + rt + (long long)J * P2; g.B = g.A; g.C = Lp + rt + rt * P2;
+        BOSIP_TRY(gemm64(ctx, g, remt, n_i, p, st));
+        const int rest = remt - n_i;
+        if (rest > 0) {
+          BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_comp[0], st));
+          BOSIP_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_comp[0], 0));
+          const long long r2 = rt + n_i;
+          g.A = Lp + r2 + (long long)J * P2; g.B = g.A; g.C = Lp + r2 + r2 * P2;
+          BOSIP_TRY(gemm64(ctx, g, rest, rest, p, sb));
+          BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_comp[1], sb));
+          big_pending = true;
+        }
       }
     }
+    if (big_pending) BOSIP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_comp[1], 0));
   } else {
     BOSIP_CUDA(ctx, cudaMemcpyAsync(dLin, L_host, (size_t)p * N * N * 8, cudaMemcpyHostToDevice, st));
     pad_L_kernel<<<dim3((P2 + 127) / 128, P2, p), 128, 0, st>>>(dLin, N, P2, Lp);
     BOSIP_CUDA(ctx, cudaGetLastError());
     for (int b = 0; b < nb; ++b) {
-      potrf_diag_kernel<<<p, 256, POTRF_SMEM, st>>>(Lp, Xp, P2, b, 0, dFlag);
+      potrf_diag_kernel<<<p, 256, POTRF_SMEM, st>>>(Lp, Xp, P2, b, 0, dFlag, nullptr);
       BOSIP_CUDA(ctx, cudaGetLastError());
     }
   }
@@ -516,6 +556,20 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   if (h_flag != 0)
     BOSIP_FAIL(ctx, BOSIP_B200_ENOTPD, "Cholesky: non-positive pivot in diagonal block " + std::to_string(h_flag - 1) +
                                          " (matrix is not positive definite)");
+
+  // the triangular solves for `a` need only L: they run on a side stream, underneath the inverse's GEMMs
+  if (!L_host) {
+    BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_in[0], st));
+    BOSIP_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_in[0], 0));
+    pad_rhs_kernel<<<dim3((P2 + 255) / 256, p), 256, 0, ss>>>(dY, N, P2, dW);
+    for (int b = 0; b < nb; ++b)
+      trsv_fwd_step<<<dim3(1 + (P2 - (b + 1) * NB + 255) / 256, p), 256, 0, ss>>>(Lp, P2, b, dW);
+    for (int b = nb - 1; b >= 0; --b)
+      trsv_bwd_step<<<dim3(1 + (b * NB + 63) / 64, p), 256, 0, ss>>>(Lp, P2, b, dW);
+    unpad_rhs_kernel<<<dim3((N + 255) / 256, p), 256, 0, ss>>>(dW, N, P2, gp->a);
+    BOSIP_CUDA(ctx, cudaGetLastError());
+    BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_in[1], ss));
+  }
 
   // ---- triangular inverse by recursive doubling: X21 = -X22 (L21 X11).  Level s pairs block [2is, 2is+s) with
   //      [2is+s, 2is+2s); when P2 is not a multiple of 2s the last pair's second block is shorter (m rows) -- one more launch.
@@ -560,15 +614,9 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
   }
 
   mark("inverse");
-  // ---- weights a = K^{-1} y: forward + backward substitution with L, one launch per 64-row block and direction
+  // ---- weights a = K^{-1} y: forward + backward substitution with L (issued above on the side stream); join here
   if (!L_host) {
-    pad_rhs_kernel<<<dim3((P2 + 255) / 256, p), 256, 0, st>>>(dY, N, P2, dW);
-    for (int b = 0; b < nb; ++b)
-      trsv_fwd_step<<<dim3(1 + (P2 - (b + 1) * NB + 255) / 256, p), 256, 0, st>>>(Lp, P2, b, dW);
-    for (int b = nb - 1; b >= 0; --b)
-      trsv_bwd_step<<<dim3(1 + (b * NB + 63) / 64, p), 256, 0, st>>>(Lp, P2, b, dW);
-    unpad_rhs_kernel<<<dim3((N + 255) / 256, p), 256, 0, st>>>(dW, N, P2, gp->a);
-    BOSIP_CUDA(ctx, cudaGetLastError());
+    BOSIP_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_in[1], 0));
   } else {
     // a_host is N x p column-major == [p][N]
     BOSIP_CUDA(ctx, cudaMemcpyAsync(gp->a, a_host, (size_t)p * N * 8, cudaMemcpyHostToDevice, st));

@@ -150,7 +150,16 @@ struct I8Args {
 // One MMA-issuing thread.  A single thread sustains ~100 clk per tcgen05.mma (descriptor arithmetic, uniform-register moves,
 // barrier polls), more than the small slice MMAs take to execute, so the slice rows of a k-block are dealt to two threads.
 // Integer accumulation is order-independent and the accumulators are handed over zeroed, so the streams need no ordering.
-template <int S, int Q, int NI>
+// PH ("phased"): every slice row a issues at most two stacked MMAs per k-step -- #1 on B positions a .. a+3 (group accumulators
+// S-1 .. S-4, the low-order ones) and #2 on positions a+4 .. S-1 (groups S-5 .. 0).  The unphased kernel issues both back to back, so
+// ALL S accumulators of an n-tile complete together and the tensor pipe idles while the epilogue drains them (~13 % of a C3 tile:
+// TMEM holds 448 of 512 columns, there is no second accumulator set).  The phased kernel walks the tile's k-blocks TWICE: phase L
+// issues every #1 (22 of the 28 slice pairs at S = 7) and commits `t_full[0]`, phase H issues every #2 (rows a < S-4 only) and commits
+// `t_full[1]`.  The epilogue drains the four low-order groups while phase H runs and the high-order groups while the NEXT tile's
+// phase L runs, so the pipe never waits for a drain.  Price: the operand tiles phase H needs (A slices 0 .. S-5, B positions
+// 4 .. S-1) are fetched a second time (+43 % L2 -> shared-memory traffic at S = 7).  Integer accumulation is exact, so the result
+// is bit-identical to the unphased kernel.  MEASURED (round 2): slower -- see launch_i8; kept as an opt-in experiment.
+template <int S, int Q, int NI, bool PH>
 __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_t sB_u, uint32_t tmem, uint64_t* a_full, uint64_t* a_empty,
                                          uint64_t* b_full, uint64_t* b_empty, uint64_t* t_full, uint64_t* t_empty) {
   using Cfg = I8Cfg<S>;
@@ -163,55 +172,62 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
       const int nkb = (t >> 1) + 1;
       // k < min(N, 64 (t + 1)) are the only non-zero columns of this n-tile: the last k-block may need fewer than 4 k-steps
       const int k_end = min(g.N, I8_BN * (t + 1));
-      for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t bs = b_cnt & 1;
-        mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1, 10 + Q);
-        const uint32_t b_lo = b_lo0 + bs * (uint32_t)(Cfg::B_SET >> 4);
-        const int nks = min(4, (k_end - kb * I8_BK + 31) >> 5);
-        int waited = S;  // groups >= waited have been claimed by this thread for this tile
 #pragma unroll
-        for (int a = S - 1; a >= 0; --a) {
-          if (Cfg::owner(a, NI) != Q) continue;
-          // slice a meets groups a .. S-1.  The epilogue hands every group back zeroed, so all MMAs accumulate and the next
-          // tile starts on the low-order groups while the previous one is still draining the high-order ones.
-          if (kb == 0) {
+      for (int phase = 0; phase < (PH ? 2 : 1); ++phase) {
+        // groups >= waited have been claimed by this thread for this tile (phase H starts below the four low-order groups)
+        int waited = (PH && phase == 1) ? S - 4 : S;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t bs = b_cnt & 1;
+          mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1, 10 + Q);
+          const uint32_t b_lo = b_lo0 + bs * (uint32_t)(Cfg::B_SET >> 4);
+          const int nks = min(4, (k_end - kb * I8_BK + 31) >> 5);
 #pragma unroll
-            for (int gi = S - 1; gi >= 0; --gi)
-              if (gi >= a && gi < waited) mbar_wait_b(&t_empty[gi], tile_cnt & 1, 100 + 10 * Q + gi);
-            if (waited == S) I8_TS(10 + Q, tile_cnt);   // first group wait of the tile satisfied
-            waited = a;
-          }
-          const uint32_t as = (uint32_t)Cfg::ring_base(Q, NI) + a_cnt % Cfg::ring(Q, NI);   // this thread's own ring
-          mbar_wait_b(&a_full[as], (a_cnt / Cfg::ring(Q, NI)) & 1, 20 + Q);
-          ++a_cnt;
-          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t a_lo = a_lo0 + as * (uint32_t)(I8_A_TILE >> 4);
-          if (kb == 0 && waited == ((Q == 0) ? S - 1 : S - 3)) I8_TS(4 + Q, tile_cnt);   // this thread's first row of the tile is about to be issued
+          for (int a = S - 1; a >= 0; --a) {
+            if (Cfg::owner(a, NI) != Q) continue;
+            if (PH && phase == 1 && a >= S - 4) continue;     // rows without a second MMA
+            // slice a meets groups a .. S-1.  The epilogue hands every group back zeroed, so all MMAs accumulate and the next
+            // tile starts on the low-order groups while the previous one is still draining the high-order ones.
+            if (kb == 0) {
+              const int lowg = (PH && phase == 0) ? (a > S - 4 ? a : S - 4) : a;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (ks < nks) {
+              for (int gi = S - 1; gi >= 0; --gi)
+                if (gi >= lowg && gi < waited) mbar_wait_b(&t_empty[gi], tile_cnt & 1, 100 + 10 * Q + gi);
+              if (waited == S) I8_TS(10 + Q, tile_cnt);   // first group wait of the tile satisfied
+              if (lowg < waited) waited = lowg;
+            }
+            const uint32_t as = (uint32_t)Cfg::ring_base(Q, NI) + a_cnt % Cfg::ring(Q, NI);   // this thread's own ring
+            mbar_wait_b(&a_full[as], (a_cnt / Cfg::ring(Q, NI)) & 1, 20 + Q);
+            ++a_cnt;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t a_lo = a_lo0 + as * (uint32_t)(I8_A_TILE >> 4);
+            if (kb == 0 && phase == 0 && waited == ((Q == 0) ? S - 1 : S - 3)) I8_TS(4 + Q, tile_cnt);   // this thread's first row of the tile is about to be issued
 #pragma unroll
-              for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> group columns 64 (c0 - a) ..
-                const int nb = (S - c0) < 4 ? (S - c0) : 4;
-                umma_i8_acc(tmem + (uint32_t)(64 * (c0 - a)), a_lo + 2 * ks, b_lo + (uint32_t)(c0 * (I8_B_TILE >> 4) + 2 * ks),
-                            umma_idesc_u8s8(I8_BM, 64 * nb));
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < nks) {
+#pragma unroll
+                for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> group columns 64 (c0 - a) ..
+                  if (PH && ((phase == 0) != (c0 == a))) continue;
+                  const int nb = (S - c0) < 4 ? (S - c0) : 4;
+                  umma_i8_acc(tmem + (uint32_t)(64 * (c0 - a)), a_lo + 2 * ks, b_lo + (uint32_t)(c0 * (I8_B_TILE >> 4) + 2 * ks),
+                              umma_idesc_u8s8(I8_BM, 64 * nb));
+                }
               }
             }
+            umma_commit(&a_empty[as]);
           }
-          umma_commit(&a_empty[as]);
+          umma_commit(&b_empty[bs]);
+          ++b_cnt;
+          if (kb == 0 && phase == 0) I8_TS(6 + Q, tile_cnt);   // first k-block of the tile issued
         }
-        umma_commit(&b_empty[bs]);
-        ++b_cnt;
-        if (kb == 0) I8_TS(6 + Q, tile_cnt);   // first k-block of the tile issued
+        umma_commit(&t_full[phase]);
       }
-      umma_commit(t_full);
       I8_TS(0 + Q, tile_cnt);                  // whole tile issued
       ++tile_cnt;
     }
   }
 }
 
-template <int S, int NI>
+template <int S, int NI, bool PH>
 __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args g) {
   using Cfg = I8Cfg<S>;
   constexpr int A_SLOTS = Cfg::A_SLOTS;
@@ -224,8 +240,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   uint64_t* a_empty = bars + A_SLOTS;       // [A_SLOTS]
   uint64_t* b_full = bars + 2 * A_SLOTS;    // [2]
   uint64_t* b_empty = b_full + 2;                // [2]
-  uint64_t* t_full = b_empty + 2;                // accumulators complete -> epilogue
-  uint64_t* t_empty = t_full + 1;                // [S] group accumulator drained and zeroed -> MMA
+  uint64_t* t_full = b_empty + 2;                // [2] accumulators complete -> epilogue ([1]: the high-order groups of the phased kernel)
+  uint64_t* t_empty = t_full + 2;                // [S] group accumulator drained and zeroed -> MMA
   __shared__ uint32_t tmem_base_s;
   __shared__ double half_sum[I8_BM];
 
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   if (tid == 0) {
     for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI); }
-    mbar_init(t_full, NI);
+    mbar_init(&t_full[0], NI); mbar_init(&t_full[1], NI);
     for (int i = 0; i < S; ++i) mbar_init(&t_empty[i], I8_EPI_WARPS);
     mbar_fence_init();
   }
@@ -262,30 +278,37 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           if (i8_subset(t, g.T64, g.nsub) != sub) continue;
           const int nkb = (t >> 1) + 1;
           const uint8_t* Bt = Bj + (size_t)i8_tile_off(t) * Cfg::B_SET;
-          for (int kb = 0; kb < nkb; ++kb) {
-            const uint32_t bs = b_cnt & 1;
-            mbar_wait_b(&b_empty[bs], ((b_cnt >> 1) & 1) ^ 1, 1);
+#pragma unroll
+          for (int phase = 0; phase < (PH ? 2 : 1); ++phase) {
+            // phase H of the phased kernel needs B positions 4 .. S-1 and A slices S-5 .. 0 only
+            const uint32_t b_off = (PH && phase == 1) ? 4u * I8_B_TILE : 0u;
+            const uint32_t b_bytes = (PH && phase == 1) ? (uint32_t)(S - 4) * I8_B_TILE : (uint32_t)Cfg::B_SET;
+            const int a_top = (PH && phase == 1) ? S - 5 : S - 1;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t bs = b_cnt & 1;
+              mbar_wait_b(&b_empty[bs], ((b_cnt >> 1) & 1) ^ 1, 1);
 #ifdef BOSIP_I8_DEBUG_NOLOAD  // bottleneck isolation: barriers only, operands stay whatever shared memory holds
-            mbar_arrive(&b_full[bs]);
+              mbar_arrive(&b_full[bs]);
 #else
-            mbar_expect_tx(&b_full[bs], Cfg::B_SET);
-            bulk_g2s(sB + (size_t)bs * Cfg::B_SET, Bt + (size_t)kb * Cfg::B_SET, Cfg::B_SET, &b_full[bs]);
+              mbar_expect_tx(&b_full[bs], b_bytes);
+              bulk_g2s(sB + (size_t)bs * Cfg::B_SET + b_off, Bt + (size_t)kb * Cfg::B_SET + b_off, b_bytes, &b_full[bs]);
 #endif
-            ++b_cnt;
-            const uint8_t* Ak = Aj + (size_t)kb * S * I8_A_TILE;
+              ++b_cnt;
+              const uint8_t* Ak = Aj + (size_t)kb * S * I8_A_TILE;
 #pragma unroll 1
-            for (int a = S - 1; a >= 0; --a) {  // least significant slice first: it only touches the accumulators the epilogue frees first
-              const int q = Cfg::owner(a, NI);
-              const uint32_t rq = (uint32_t)Cfg::ring(q, NI);
-              const uint32_t as = (uint32_t)Cfg::ring_base(q, NI) + a_cnt[q] % rq;
-              mbar_wait_b(&a_empty[as], ((a_cnt[q] / rq) & 1) ^ 1, 2);
+              for (int a = a_top; a >= 0; --a) {  // least significant slice first: it only touches the accumulators the epilogue frees first
+                const int q = Cfg::owner(a, NI);
+                const uint32_t rq = (uint32_t)Cfg::ring(q, NI);
+                const uint32_t as = (uint32_t)Cfg::ring_base(q, NI) + a_cnt[q] % rq;
+                mbar_wait_b(&a_empty[as], ((a_cnt[q] / rq) & 1) ^ 1, 2);
 #ifdef BOSIP_I8_DEBUG_NOLOAD
-              mbar_arrive(&a_full[as]);
+                mbar_arrive(&a_full[as]);
 #else
-              mbar_expect_tx(&a_full[as], I8_A_TILE);
-              bulk_g2s(sA + (size_t)as * I8_A_TILE, Ak + (size_t)a * I8_A_TILE, I8_A_TILE, &a_full[as]);
+                mbar_expect_tx(&a_full[as], I8_A_TILE);
+                bulk_g2s(sA + (size_t)as * I8_A_TILE, Ak + (size_t)a * I8_A_TILE, I8_A_TILE, &a_full[as]);
 #endif
-              ++a_cnt[q];
+                ++a_cnt[q];
+              }
             }
           }
         }
@@ -294,8 +317,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   } else if (warp == 1 || warp == 10) {
     // ================================================================ MMA issuers (one thread each, disjoint slice rows)
     if (lane == 0) {
-      if (warp == 1) i8_issue<S, 0, NI>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
-      else if (NI > 1) i8_issue<S, 1, NI>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      if (warp == 1) i8_issue<S, 0, NI, PH>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      else if (NI > 1) i8_issue<S, 1, NI, PH>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
     }
   } else {
     // ================================================================ epilogue: 8 warps, thread = (row, 32-column half)
@@ -320,7 +343,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
       double rs = 0.0;
       for (int t = g.T64 - 1; t >= 0; --t) {
         if (i8_subset(t, g.T64, g.nsub) != sub) continue;
-        mbar_wait_b(t_full, tile_cnt & 1, 30);
+        mbar_wait_b(&t_full[0], tile_cnt & 1, 30);   // phased kernel: the four low-order groups; otherwise all of them
         if (tid == 64) I8_TS(2, tile_cnt);       // accumulators complete
         if (lane == 0) I8_TW(0, ew, tile_cnt);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -340,6 +363,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           long long acc[32];
 #pragma unroll
           for (int gi = S - 1; gi >= 0; --gi) {
+            if (PH && gi == S - 5) {               // the high-order groups complete with phase H
+              mbar_wait_b(&t_full[1], tile_cnt & 1, 31);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
             const uint32_t ta = taddr + (uint32_t)(64 * (S - 1 - gi));
             tmem_ld32(ta, v);
             tmem_zero32(ta);
@@ -373,6 +400,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           double w[32];
 #pragma unroll
           for (int gi = S - 1; gi >= 0; --gi) {
+            if (PH && gi == S - 5) {
+              mbar_wait_b(&t_full[1], tile_cnt & 1, 31);
+              asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            }
             const uint32_t ta = taddr + (uint32_t)(64 * (S - 1 - gi));
             tmem_ld32(ta, v);
             tmem_zero32(ta);
@@ -521,11 +552,11 @@ int i8_nsub(const Gp* gp) {
   return nsub > T64 ? T64 : nsub;
 }
 
-template <int S, int NI>
+template <int S, int NI, bool PH>
 static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   const int grid = a.n_items < ctx->sms ? a.n_items : ctx->sms;
-  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
-  vargemm_i8_kernel<S, NI><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
+  vargemm_i8_kernel<S, NI, PH><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
   {
@@ -594,6 +625,11 @@ __global__ void i8_cmp_kernel(const unsigned long long* __restrict__ x, const un
 // issuer (~10 % slower).  BOSIP_B200_I8_ISSUERS=1 / 2 forces the choice (2: no self-check; development only).
 template <int S>
 static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
+  // BOSIP_B200_I8_PHASED=1 selects the phased kernel (development A/B switch; both give bit-identical results).  It is OFF by
+  // default: measured on B200 at C3 (profiles/r02_phased_ab.json) it is 23 % SLOWER, 3.94 vs 3.20 ms per launch -- phase H streams
+  // 72 KB of operands per k-block for only ~870 clk of MMA work (85 B/clk per SM against the 44 B/clk of the unphased kernel), so the
+  // TMA feed, not the drain it removes, becomes the limiter.
+  static const bool phased = getenv("BOSIP_B200_I8_PHASED") && atoi(getenv("BOSIP_B200_I8_PHASED")) == 1;
   if (ctx->i8_issuers == 0) {
     const char* e = getenv("BOSIP_B200_I8_ISSUERS");
     const int forced = e ? atoi(e) : 0;
@@ -607,8 +643,9 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       unsigned int* d_mis = reinterpret_cast<unsigned int*>(ref + n);
       BOSIP_CUDA(ctx, cudaMemsetAsync(d_mis, 0, 8, st));
       I8Args b = a; b.q_part = ref;
-      BOSIP_TRY((launch_i8n<S, 1>(ctx, b, st)));
-      BOSIP_TRY((launch_i8n<S, I8_ISSUERS>(ctx, a, st)));
+      BOSIP_TRY((launch_i8n<S, 1, false>(ctx, b, st)));            // the reference: one issuer, all accumulators complete together
+      if (phased) BOSIP_TRY((launch_i8n<S, I8_ISSUERS, true>(ctx, a, st)));
+      else BOSIP_TRY((launch_i8n<S, I8_ISSUERS, false>(ctx, a, st)));
       i8_cmp_kernel<<<ctx->sms * 4, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(ref), reinterpret_cast<const unsigned long long*>(a.q_part),
                                                    a.mc, (long long)a.m_tiles * I8_BM, a.nsub * a.p, d_mis);
       BOSIP_CUDA(ctx, cudaGetLastError());
@@ -627,7 +664,8 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       return 0;
     }
   }
-  return ctx->i8_issuers == 1 ? launch_i8n<S, 1>(ctx, a, st) : launch_i8n<S, I8_ISSUERS>(ctx, a, st);
+  if (ctx->i8_issuers == 1) return phased ? launch_i8n<S, 1, true>(ctx, a, st) : launch_i8n<S, 1, false>(ctx, a, st);
+  return phased ? launch_i8n<S, I8_ISSUERS, true>(ctx, a, st) : launch_i8n<S, I8_ISSUERS, false>(ctx, a, st);
 }
 
 // Ks8: [p][mc/128][KB][S][16 KB]; q_part: [nsub][p][mc] scratch; q: [p][mc]
