@@ -501,20 +501,35 @@ def main():
         step_device()
     ev_pairs.clear()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()                                                  # every rank samples its own GPU's clocks
     ctx.timing_reset(True)
     l0 = ctx.launch_count()
     ms_total, _ = H.timed(step_device, args.steps)
     launches = ctx.launch_count() - l0
     tm = ctx.timing_get(); ctx.timing_reset(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     winner = gather.result()
     value = args.steps * per_rank_total / (ms_total * 1e-3)          # whole-job aggregate over all ranks
     comp_ms = sum(e[0].elapsed_time(e[1]) for e in ev_pairs) / args.steps
     gath_ms = sum(e[1].elapsed_time(e[2]) for e in ev_pairs) / args.steps
     breakdown = {"compute_ms": comp_ms, "argmax_exchange_ms": gath_ms, "other_ms": ms_total / args.steps - comp_ms - gath_ms,
                  "note": "this rank's device times per step: fused sweep | device all-gather of the winners | rest (launch gaps, the max over ranks)"}
+    if world > 1:   # what limits the N-GPU step: every rank's own compute time and clocks, side by side
+        mine = torch.tensor([comp_ms, gath_ms, (clocks or {}).get("sm_mhz") or 0.0, (clocks or {}).get("power_w_max") or 0.0],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        tab = torch.stack(allr).cpu().numpy()
+        cmin, cmax = float(tab[:, 0].min()), float(tab[:, 0].max())
+        spread = cmax - cmin
+        exch = float(tab[:, 1].max())
+        breakdown["per_rank"] = {"compute_ms": [float(v) for v in tab[:, 0]], "argmax_exchange_ms": [float(v) for v in tab[:, 1]],
+                                 "sm_mhz": [float(v) for v in tab[:, 2]], "power_w_max": [float(v) for v in tab[:, 3]]}
+        breakdown["limiter"] = (
+            f"compute on the slowest rank: {cmax:.1f} ms against {cmin:.1f} ms on the fastest (spread {100 * spread / cmax:.2f} % of the step; every rank "
+            f"runs the same kernels on the same amount of work at its own power-capped clock), against {exch:.3f} ms for the 16-byte argmax exchange "
+            f"({100 * exch / cmax:.3f} %)" if spread >= exch else
+            f"the argmax exchange ({exch:.3f} ms) exceeds the compute spread between ranks ({spread:.3f} ms)")
 
     # ---- end to end through the public API with HOST buffers: pinned, then pageable (what Julia's Array{Float64} is)
     Xh_t = torch.empty((count, pr.d), dtype=torch.float64).pin_memory()

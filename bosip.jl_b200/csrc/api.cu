@@ -457,11 +457,22 @@ static int set_fits(Ctx* ctx, Sweep& sw, bosip_b200_gp* const* gps, int n, const
 
 using namespace bosip;
 
+// Makes the context's device current for the duration of an entry point and restores the caller's device afterwards: a host that
+// drives several contexts from one thread (bosip_b200_init_multi, or a framework with its own notion of "current device" such as
+// torch) must not find its device changed behind its back.
+struct DeviceScope {
+  int prev = -1;
+  bool ok;
+  explicit DeviceScope(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; ok = cudaSetDevice(dev) == cudaSuccess; }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define API_LOCK(ctxp)                        \
   if (!(ctxp)) return BOSIP_B200_EINVAL;      \
   Ctx* ctx = &(ctxp)->c;                      \
   std::lock_guard<std::mutex> lock__(ctx->mu); \
-  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return BOSIP_B200_ECUDA; }
+  DeviceScope dev_scope__(ctx->device);       \
+  if (!dev_scope__.ok) { ctx->err = "cudaSetDevice failed"; return BOSIP_B200_ECUDA; }
 
 extern "C" {
 
@@ -480,7 +491,9 @@ int bosip_b200_init(int device, bosip_b200_ctx** out) {
   }
   if (device < 0 || device >= ndev) { g_init_error = "device index out of range"; return BOSIP_B200_EINVAL; }
   cudaDeviceProp prop;
-  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+  DeviceScope dev_scope(device);   // the caller's current device is restored on every return path
+  if (!dev_scope.ok || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    if (!dev_scope.ok) e = cudaGetLastError();
     g_init_error = std::string("cudaSetDevice/GetDeviceProperties: ") + cudaGetErrorString(e);
     return BOSIP_B200_ECUDA;
   }
@@ -515,7 +528,7 @@ int bosip_b200_init(int device, bosip_b200_ctx** out) {
 int bosip_b200_shutdown(bosip_b200_ctx* h) {
   if (!h) return BOSIP_B200_EINVAL;
   Ctx* ctx = &h->c;
-  cudaSetDevice(ctx->device);
+  DeviceScope dev_scope(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -624,7 +637,7 @@ int bosip_b200_gp_free(bosip_b200_gp* gh) {
   if (gh->g) {
     bosip_b200_ctx* h = reinterpret_cast<bosip_b200_ctx*>(gh->g->ctx);
     std::lock_guard<std::mutex> lock(h->c.mu);
-    cudaSetDevice(h->c.device);
+    DeviceScope dev_scope(h->c.device);
     gp_destroy(gh->g);
   }
   delete gh;
