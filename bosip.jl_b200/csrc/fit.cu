@@ -268,11 +268,13 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap
 // exactly (warp 0: two rows per lane, the pivot row's value broadcast by shuffle, multiplied by the reciprocal diagonal, which is
 // formed once per block by 64 parallel divisions -- redundant across CTAs, which
 // costs nothing but keeps the step to ONE kernel), CTA 0 stores the block's solution, CTA c >= 1 applies the block's solution
-// to its share of the remaining right-hand side (a GEMV slab with coalesced reads).  rhs is [p][P], zero padded.
+// to its share of the remaining right-hand side (a GEMV slab with coalesced reads).  rhs and sol are [p][P], zero padded; the
+// block's solution goes to a SEPARATE array: the other CTAs of the launch still read the block's right-hand side.
 __device__ __forceinline__ void trsv_load_block(const double* __restrict__ L, int P, int r0, double (*D)[65]) {
   for (int e = threadIdx.x; e < 64 * 64; e += 256) { const int rr = e & 63, cc = e >> 6; D[rr][cc] = L[(size_t)(r0 + rr) + (size_t)(r0 + cc) * P]; }
 }
-__global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ Lp, int P, int b, double* __restrict__ rhs) {
+__global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ Lp, int P, int b, double* __restrict__ rhs,
+                                                     double* __restrict__ sol) {
   __shared__ double D[64][65];
   __shared__ double w[64];
   const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r0 = b * 64;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ 
     w[lane] = x0; w[lane + 32] = x1;
   }
   __syncthreads();
-  if (blockIdx.x == 0) { if (tid < 64) y[r0 + tid] = w[tid]; return; }
+  if (blockIdx.x == 0) { if (tid < 64) sol[(size_t)j * P + r0 + tid] = w[tid]; return; }
   const int row = r0 + 64 + (blockIdx.x - 1) * 256 + tid;
   if (row >= P) return;
   const double* Lr = L + (size_t)row + (size_t)r0 * P;
@@ -304,7 +306,8 @@ __global__ void __launch_bounds__(256) trsv_fwd_step(const double* __restrict__ 
   for (int k = 0; k < 64; ++k) acc = fma(Lr[(size_t)k * P], w[k], acc);
   y[row] -= acc;
 }
-__global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ Lp, int P, int b, double* __restrict__ rhs) {
+__global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ Lp, int P, int b, double* __restrict__ rhs,
+                                                     double* __restrict__ sol) {
   __shared__ double D[64][65];
   __shared__ double a[64];
   const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r0 = b * 64;
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(256) trsv_bwd_step(const double* __restrict__ 
     a[lane] = x0; a[lane + 32] = x1;
   }
   __syncthreads();
-  if (blockIdx.x == 0) { if (tid < 64) w[r0 + tid] = a[tid]; return; }
+  if (blockIdx.x == 0) { if (tid < 64) sol[(size_t)j * P + r0 + tid] = a[tid]; return; }
   // rows jj < r0 of the transposed system: w[jj] -= sum_k L[r0 + k][jj] a[k]; one warp per row, lanes along k (contiguous in memory)
   const double a0 = a[lane], a1 = a[lane + 32];
   for (int q = 0; q < 8; ++q) {
@@ -451,7 +454,7 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     gp->Us = G(o_Us); gp->scale = G(o_scale); gp->As = G(o_As); gp->LinvT = G(o_LinvT); gp->L = G(o_L); gp->Linv = G(o_Linv); gp->a = G(o_a);
     // temporaries of the factorisation: the context's grow-only workspace (no allocation after the first fit of a size)
     off = 0;
-    const size_t w_X = carve((size_t)d * N), w_alpha = carve(p), w_diag = carve(p), w_floor = carve(p), w_Y = carve((size_t)p * N), w_W = carve((size_t)p * P2),
+    const size_t w_X = carve((size_t)d * N), w_alpha = carve(p), w_diag = carve(p), w_floor = carve(p), w_Y = carve((size_t)p * N), w_W = carve((size_t)3 * p * P2),
                  w_Lp = carve(pp), w_Xp = carve(pp), w_Tmp = carve((size_t)p * ((size_t)P2 * P2 / 2 + (size_t)64 * P2)),
                  w_Lin = L_host ? carve((size_t)p * N * N) : 0, w_flag = carve(1);
     BOSIP_TRY(ensure_ws(ctx, off));
@@ -563,10 +566,10 @@ int gp_build(Ctx* ctx, int kernel_id, int d, int N, int p, const double* X, cons
     BOSIP_CUDA(ctx, cudaStreamWaitEvent(ss, ctx->ev_in[0], 0));
     pad_rhs_kernel<<<dim3((P2 + 255) / 256, p), 256, 0, ss>>>(dY, N, P2, dW);
     for (int b = 0; b < nb; ++b)
-      trsv_fwd_step<<<dim3(1 + (P2 - (b + 1) * NB + 255) / 256, p), 256, 0, ss>>>(Lp, P2, b, dW);
+      trsv_fwd_step<<<dim3(1 + (P2 - (b + 1) * NB + 255) / 256, p), 256, 0, ss>>>(Lp, P2, b, dW, dW + (size_t)p * P2);
     for (int b = nb - 1; b >= 0; --b)
-      trsv_bwd_step<<<dim3(1 + (b * NB + 63) / 64, p), 256, 0, ss>>>(Lp, P2, b, dW);
-    unpad_rhs_kernel<<<dim3((N + 255) / 256, p), 256, 0, ss>>>(dW, N, P2, gp->a);
+      trsv_bwd_step<<<dim3(1 + (b * NB + 63) / 64, p), 256, 0, ss>>>(Lp, P2, b, dW + (size_t)p * P2, dW + (size_t)2 * p * P2);
+    unpad_rhs_kernel<<<dim3((N + 255) / 256, p), 256, 0, ss>>>(dW + (size_t)2 * p * P2, N, P2, gp->a);
     BOSIP_CUDA(ctx, cudaGetLastError());
     BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_in[1], ss));
   }

@@ -29,6 +29,7 @@ constexpr int I8_B_TILE = I8_BN * I8_BK;  //  8 KB: [ 64 rows][128 B], SWIZZLE_1
 constexpr int I8_THREADS = 352;   // warp 0 TMA producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
 constexpr int I8_ISSUERS = 2;      // MMA-issuing threads of the default kernel; NI = 1 is kept as a cross-check (BOSIP_B200_I8_ISSUERS=1)
 constexpr int I8_EPI_WARPS = 8;
+constexpr int I8_DEFAULT_MODE = 0;  // MMA schedule of the default kernel (see i8_issue): 0 plain, 1 phased, 2 split last k-block
 
 template <int S> struct I8Cfg {
   // which of the two MMA threads issues slice a (a row of the slice-pair triangle); balanced in MMA count per k-step
@@ -159,7 +160,12 @@ struct I8Args {
 // phase L runs, so the pipe never waits for a drain.  Price: the operand tiles phase H needs (A slices 0 .. S-5, B positions
 // 4 .. S-1) are fetched a second time (+43 % L2 -> shared-memory traffic at S = 7).  Integer accumulation is exact, so the result
 // is bit-identical to the unphased kernel.  MEASURED (round 2): slower -- see launch_i8; kept as an opt-in experiment.
-template <int S, int Q, int NI, bool PH>
+// MD = 2 ("split last k-block") takes the idea without the re-fetch: only in the LAST k-block of a tile the #2 MMAs (rows a < S-4)
+// are deferred until every #1 has been issued and `t_full[0]` committed; their A tiles simply stay in their ring slots a little
+// longer.  The epilogue then starts draining the low-order groups while the tensor pipe still works on the deferred #2s (~870 clk
+// at S = 7), and the next tile's first rows find their accumulators released when the pipe gets to them.
+// MD: 0 = plain, 1 = phased, 2 = split last k-block.
+template <int S, int Q, int NI, int MD>
 __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_t sB_u, uint32_t tmem, uint64_t* a_full, uint64_t* a_empty,
                                          uint64_t* b_full, uint64_t* b_empty, uint64_t* t_full, uint64_t* t_empty) {
   using Cfg = I8Cfg<S>;
@@ -172,6 +178,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
       const int nkb = (t >> 1) + 1;
       // k < min(N, 64 (t + 1)) are the only non-zero columns of this n-tile: the last k-block may need fewer than 4 k-steps
       const int k_end = min(g.N, I8_BN * (t + 1));
+      constexpr bool PH = (MD == 1);
 #pragma unroll
       for (int phase = 0; phase < (PH ? 2 : 1); ++phase) {
         // groups >= waited have been claimed by this thread for this tile (phase H starts below the four low-order groups)
@@ -181,6 +188,8 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
           mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1, 10 + Q);
           const uint32_t b_lo = b_lo0 + bs * (uint32_t)(Cfg::B_SET >> 4);
           const int nks = min(4, (k_end - kb * I8_BK + 31) >> 5);
+          const bool split = (MD == 2) && (kb == nkb - 1);     // last k-block: #1 MMAs of every row first, the #2 MMAs afterwards
+          uint32_t hold_as[S], hold_lo[S];                      // ring slot / descriptor of the rows whose #2 MMA is deferred
 #pragma unroll
           for (int a = S - 1; a >= 0; --a) {
             if (Cfg::owner(a, NI) != Q) continue;
@@ -207,19 +216,34 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
 #pragma unroll
                 for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> group columns 64 (c0 - a) ..
                   if (PH && ((phase == 0) != (c0 == a))) continue;
+                  if (MD == 2 && split && c0 != a) continue;
                   const int nb = (S - c0) < 4 ? (S - c0) : 4;
                   umma_i8_acc(tmem + (uint32_t)(64 * (c0 - a)), a_lo + 2 * ks, b_lo + (uint32_t)(c0 * (I8_B_TILE >> 4) + 2 * ks),
                               umma_idesc_u8s8(I8_BM, 64 * nb));
                 }
               }
             }
-            umma_commit(&a_empty[as]);
+            if (MD == 2 && split && a < S - 4) { hold_as[a] = as; hold_lo[a] = a_lo; }
+            else umma_commit(&a_empty[as]);
+          }
+          if (MD == 2 && split) {
+            umma_commit(&t_full[0]);                           // the low-order groups are complete once these MMAs retire
+#pragma unroll
+            for (int a = S - 5; a >= 0; --a) {
+              if (Cfg::owner(a, NI) != Q) continue;
+              const int c0 = a + 4, nb = S - c0;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                if (ks < nks)
+                  umma_i8_acc(tmem + 256u, hold_lo[a] + 2 * ks, b_lo + (uint32_t)(c0 * (I8_B_TILE >> 4) + 2 * ks), umma_idesc_u8s8(I8_BM, 64 * nb));
+              umma_commit(&a_empty[hold_as[a]]);
+            }
           }
           umma_commit(&b_empty[bs]);
           ++b_cnt;
           if (kb == 0 && phase == 0) I8_TS(6 + Q, tile_cnt);   // first k-block of the tile issued
         }
-        umma_commit(&t_full[phase]);
+        umma_commit(&t_full[MD == 2 ? 1 : phase]);
       }
       I8_TS(0 + Q, tile_cnt);                  // whole tile issued
       ++tile_cnt;
@@ -227,8 +251,9 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
   }
 }
 
-template <int S, int NI, bool PH>
+template <int S, int NI, int MD>
 __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args g) {
+  constexpr bool PH = (MD == 1);
   using Cfg = I8Cfg<S>;
   constexpr int A_SLOTS = Cfg::A_SLOTS;
   extern __shared__ unsigned char smem_raw[];
@@ -317,8 +342,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   } else if (warp == 1 || warp == 10) {
     // ================================================================ MMA issuers (one thread each, disjoint slice rows)
     if (lane == 0) {
-      if (warp == 1) i8_issue<S, 0, NI, PH>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
-      else if (NI > 1) i8_issue<S, 1, NI, PH>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      if (warp == 1) i8_issue<S, 0, NI, MD>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      else if (NI > 1) i8_issue<S, 1, NI, MD>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
     }
   } else {
     // ================================================================ epilogue: 8 warps, thread = (row, 32-column half)
@@ -363,7 +388,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           long long acc[32];
 #pragma unroll
           for (int gi = S - 1; gi >= 0; --gi) {
-            if (PH && gi == S - 5) {               // the high-order groups complete with phase H
+            if (MD != 0 && gi == S - 5) {          // the high-order groups complete with phase H / the deferred MMAs
               mbar_wait_b(&t_full[1], tile_cnt & 1, 31);
               asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
@@ -400,7 +425,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
           double w[32];
 #pragma unroll
           for (int gi = S - 1; gi >= 0; --gi) {
-            if (PH && gi == S - 5) {
+            if (MD != 0 && gi == S - 5) {
               mbar_wait_b(&t_full[1], tile_cnt & 1, 31);
               asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             }
@@ -552,11 +577,11 @@ int i8_nsub(const Gp* gp) {
   return nsub > T64 ? T64 : nsub;
 }
 
-template <int S, int NI, bool PH>
+template <int S, int NI, int MD>
 static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   const int grid = a.n_items < ctx->sms ? a.n_items : ctx->sms;
-  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
-  vargemm_i8_kernel<S, NI, PH><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
+  vargemm_i8_kernel<S, NI, MD><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
   {
@@ -608,6 +633,13 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   return 0;
 }
 
+template <int S, int NI>
+static int launch_i8m(Ctx* ctx, const I8Args& a, int mode, cudaStream_t st) {
+  if (mode == 1) return launch_i8n<S, NI, 1>(ctx, a, st);
+  if (mode == 2) return launch_i8n<S, NI, 2>(ctx, a, st);
+  return launch_i8n<S, NI, 0>(ctx, a, st);
+}
+
 // bitwise comparison of the rows the GEMM wrote: part[(u * p + j) * mc + r], r < rows
 __global__ void i8_cmp_kernel(const unsigned long long* __restrict__ x, const unsigned long long* __restrict__ y, long long mc, long long rows,
                               int nvec, unsigned int* __restrict__ mismatches) {
@@ -625,11 +657,11 @@ __global__ void i8_cmp_kernel(const unsigned long long* __restrict__ x, const un
 // issuer (~10 % slower).  BOSIP_B200_I8_ISSUERS=1 / 2 forces the choice (2: no self-check; development only).
 template <int S>
 static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
-  // BOSIP_B200_I8_PHASED=1 selects the phased kernel (development A/B switch; both give bit-identical results).  It is OFF by
-  // default: measured on B200 at C3 (profiles/r02_phased_ab.json) it is 23 % SLOWER, 3.94 vs 3.20 ms per launch -- phase H streams
-  // 72 KB of operands per k-block for only ~870 clk of MMA work (85 B/clk per SM against the 44 B/clk of the unphased kernel), so the
-  // TMA feed, not the drain it removes, becomes the limiter.
-  static const bool phased = getenv("BOSIP_B200_I8_PHASED") && atoi(getenv("BOSIP_B200_I8_PHASED")) == 1;
+  // BOSIP_B200_I8_MODE selects the MMA schedule (development A/B switch; all three give bit-identical results): 0 plain, 1 phased,
+  // 2 split last k-block.  The phased kernel is 23 % SLOWER on B200 at C3 (profiles/r02_phased_ab.json: 3.94 vs 3.20 ms per launch --
+  // phase H streams 72 KB of operands per k-block for only ~870 clk of MMA work, 85 B/clk per SM against 44 B/clk, so the TMA feed,
+  // not the drain it removes, becomes the limiter).
+  static const int mode = getenv("BOSIP_B200_I8_MODE") ? atoi(getenv("BOSIP_B200_I8_MODE")) : I8_DEFAULT_MODE;
   if (ctx->i8_issuers == 0) {
     const char* e = getenv("BOSIP_B200_I8_ISSUERS");
     const int forced = e ? atoi(e) : 0;
@@ -643,9 +675,8 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       unsigned int* d_mis = reinterpret_cast<unsigned int*>(ref + n);
       BOSIP_CUDA(ctx, cudaMemsetAsync(d_mis, 0, 8, st));
       I8Args b = a; b.q_part = ref;
-      BOSIP_TRY((launch_i8n<S, 1, false>(ctx, b, st)));            // the reference: one issuer, all accumulators complete together
-      if (phased) BOSIP_TRY((launch_i8n<S, I8_ISSUERS, true>(ctx, a, st)));
-      else BOSIP_TRY((launch_i8n<S, I8_ISSUERS, false>(ctx, a, st)));
+      BOSIP_TRY((launch_i8n<S, 1, 0>(ctx, b, st)));                // the reference: one issuer, plain schedule
+      BOSIP_TRY((launch_i8m<S, I8_ISSUERS>(ctx, a, mode, st)));
       i8_cmp_kernel<<<ctx->sms * 4, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(ref), reinterpret_cast<const unsigned long long*>(a.q_part),
                                                    a.mc, (long long)a.m_tiles * I8_BM, a.nsub * a.p, d_mis);
       BOSIP_CUDA(ctx, cudaGetLastError());
@@ -664,8 +695,7 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       return 0;
     }
   }
-  if (ctx->i8_issuers == 1) return phased ? launch_i8n<S, 1, true>(ctx, a, st) : launch_i8n<S, 1, false>(ctx, a, st);
-  return phased ? launch_i8n<S, I8_ISSUERS, true>(ctx, a, st) : launch_i8n<S, I8_ISSUERS, false>(ctx, a, st);
+  return ctx->i8_issuers == 1 ? launch_i8m<S, 1>(ctx, a, mode, st) : launch_i8m<S, I8_ISSUERS>(ctx, a, mode, st);
 }
 
 // Ks8: [p][mc/128][KB][S][16 KB]; q_part: [nsub][p][mc] scratch; q: [p][mc]

@@ -166,6 +166,33 @@ def test_two_mma_issuers_equal_one_bit_for_bit(bb, ctx, engine, tmp_path):
     assert np.array_equal(np.load(out), var2)
 
 
+@pytest.mark.parametrize("slices", [6, 7, 8])
+def test_mma_schedules_are_bit_identical(bb, ctx, engine, tmp_path, slices):
+    """The three MMA schedules of the INT8 kernel (BOSIP_B200_I8_MODE: 0 plain, 1 phased, 2 split last k-block; vargemm_i8.cu) only
+    reorder exact integer accumulations: every slice count must give the same bits, on a shape with a ragged last tile and tiles of
+    one to several k-blocks.  The mode is read at first use, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    outs = []
+    for mode in (0, 1, 2):
+        out = tmp_path / f"var_m{mode}.npy"
+        code = (
+            "import sys, numpy as np\n"
+            f"sys.path.insert(0, {repr(root)})\n"
+            "import bosip_b200 as bb\n"
+            f"ctx = bb.Context(0); ctx.set_variance_engine('int8', {slices})\n"
+            "pr = bb.synth.make_problem('X', d=4, p=2, N=715, seed=77)\n"
+            "model = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma)\n"
+            "Xq = np.random.default_rng(5).uniform(pr.lb[:, None], pr.ub[:, None], size=(pr.d, 3001))\n"
+            "post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)\n"
+            f"np.save({repr(str(out))}, post.mean_and_var(Xq)[1]); assert ctx.i8_issuers() == 2\n")
+        subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, BOSIP_B200_I8_MODE=str(mode)), timeout=300)
+        outs.append(np.load(out))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
 @pytest.mark.parametrize("d,p,N,M,kernel_id", [(10, 1, 4096, 1500, 2), (4, 2, 2000, 1000, 1), (3, 3, 1025, 700, 0)])
 def test_int8_large_training_sets(bb, ctx, engine, d, p, N, M, kernel_id):
     """Deep contractions (BASELINE config 5: N = 4096, d = 10) and sizes just past a tile edge: many k-blocks per n-tile, several
@@ -186,3 +213,13 @@ def test_int8_large_training_sets(bb, ctx, engine, d, p, N, M, kernel_id):
     kxx = alpha ** 2
     assert _var_err(var, ovar, kxx) < TOL and _var_err(var, var64, kxx) < TOL
     assert _var_err(var, ovar, kxx) < 4 * _var_err(var64, ovar, kxx) + 1e-12
+    # the weights a = K^-1 y come from the stepwise triangular solves (64 block steps per direction at N = 4096, many CTAs per step):
+    # a and the mean against the oracle at these sizes too
+    ag = post.factors()[2]
+    assert np.max(np.abs(ag - ofit.a)) / np.max(np.abs(ofit.a)) < 1e-10
+    # mu = k* . a is a cancelling sum when the targets are noise (Y ~ N(0, 1) here: |a| ~ |y| / sigma^2 while |mu| = O(1)), so the
+    # bound is the one the agreement of `a` implies: 1e-10 of max|a| on every term of the dot product, on top of 1e-10 relative
+    for j in range(p):
+        Ks = alpha[j] ** 2 * orc.cross_kernel(kernel_id, Xq, X, lam[:, j])            # M x N
+        bound = TOL * (np.abs(omu[j]) + 1e-3 * np.max(np.abs(omu))) + TOL * np.max(np.abs(ofit.a[:, j])) * np.abs(Ks).sum(axis=1)
+        assert np.all(np.abs(mu[j] - omu[j]) <= bound), float(np.max(np.abs(mu[j] - omu[j]) / bound))
