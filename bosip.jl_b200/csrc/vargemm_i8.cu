@@ -164,7 +164,9 @@ struct I8Args {
 // are deferred until every #1 has been issued and `t_full[0]` committed; their A tiles simply stay in their ring slots a little
 // longer.  The epilogue then starts draining the low-order groups while the tensor pipe still works on the deferred #2s (~870 clk
 // at S = 7), and the next tile's first rows find their accumulators released when the pipe gets to them.
-// MD: 0 = plain, 1 = phased, 2 = split last k-block.
+// MD = 3 additionally splits the FIRST k-block: all #1 MMAs of the new tile need the low-order groups only (which the epilogue
+// releases first), the #2 MMAs -- the only ones that touch the high-order groups -- go to the end of the k-block.
+// MD: 0 = plain, 1 = phased, 2 = split last k-block, 3 = split first and last k-block.
 template <int S, int Q, int NI, int MD>
 __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_t sB_u, uint32_t tmem, uint64_t* a_full, uint64_t* a_empty,
                                          uint64_t* b_full, uint64_t* b_empty, uint64_t* t_full, uint64_t* t_empty) {
@@ -181,14 +183,18 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
       constexpr bool PH = (MD == 1);
 #pragma unroll
       for (int phase = 0; phase < (PH ? 2 : 1); ++phase) {
-        // groups >= waited have been claimed by this thread for this tile (phase H starts below the four low-order groups)
+        // groups >= waited have been claimed by this thread for this tile (phase H starts below the four low-order groups);
+        // waited_h does the same for the high-order groups of a split first k-block (MD = 3)
         int waited = (PH && phase == 1) ? S - 4 : S;
+        int waited_h = S - 4;
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t bs = b_cnt & 1;
           mbar_wait_b(&b_full[bs], (b_cnt >> 1) & 1, 10 + Q);
           const uint32_t b_lo = b_lo0 + bs * (uint32_t)(Cfg::B_SET >> 4);
           const int nks = min(4, (k_end - kb * I8_BK + 31) >> 5);
-          const bool split = (MD == 2) && (kb == nkb - 1);     // last k-block: #1 MMAs of every row first, the #2 MMAs afterwards
+          // split k-block: the #1 MMAs of every row first, the #2 MMAs (rows a < S-4) afterwards.  MD = 2: the last k-block of a
+          // tile; MD = 3: the first one as well
+          const bool split = (MD >= 2) && (kb == nkb - 1 || (MD == 3 && kb == 0));
           uint32_t hold_as[S], hold_lo[S];                      // ring slot / descriptor of the rows whose #2 MMA is deferred
 #pragma unroll
           for (int a = S - 1; a >= 0; --a) {
@@ -197,7 +203,8 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
             // slice a meets groups a .. S-1.  The epilogue hands every group back zeroed, so all MMAs accumulate and the next
             // tile starts on the low-order groups while the previous one is still draining the high-order ones.
             if (kb == 0) {
-              const int lowg = (PH && phase == 0) ? (a > S - 4 ? a : S - 4) : a;
+              const bool low_only = (PH && phase == 0) || (MD == 3);     // this row's #1 MMA needs the low-order groups only
+              const int lowg = low_only ? (a > S - 4 ? a : S - 4) : a;
 #pragma unroll
               for (int gi = S - 1; gi >= 0; --gi)
                 if (gi >= lowg && gi < waited) mbar_wait_b(&t_empty[gi], tile_cnt & 1, 100 + 10 * Q + gi);
@@ -216,21 +223,27 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
 #pragma unroll
                 for (int c0 = a; c0 < S; c0 += 4) {  // slice positions c0 .. c0+nb-1 (descending b) -> group columns 64 (c0 - a) ..
                   if (PH && ((phase == 0) != (c0 == a))) continue;
-                  if (MD == 2 && split && c0 != a) continue;
+                  if (MD >= 2 && split && c0 != a) continue;
                   const int nb = (S - c0) < 4 ? (S - c0) : 4;
                   umma_i8_acc(tmem + (uint32_t)(64 * (c0 - a)), a_lo + 2 * ks, b_lo + (uint32_t)(c0 * (I8_B_TILE >> 4) + 2 * ks),
                               umma_idesc_u8s8(I8_BM, 64 * nb));
                 }
               }
             }
-            if (MD == 2 && split && a < S - 4) { hold_as[a] = as; hold_lo[a] = a_lo; }
+            if (MD >= 2 && split && a < S - 4) { hold_as[a] = as; hold_lo[a] = a_lo; }
             else umma_commit(&a_empty[as]);
           }
-          if (MD == 2 && split) {
-            umma_commit(&t_full[0]);                           // the low-order groups are complete once these MMAs retire
+          if (MD >= 2 && split) {
+            if (kb == nkb - 1) umma_commit(&t_full[0]);        // the low-order groups are complete once these MMAs retire
 #pragma unroll
             for (int a = S - 5; a >= 0; --a) {
               if (Cfg::owner(a, NI) != Q) continue;
+              if (MD == 3 && kb == 0) {                        // the deferred #2 MMAs are the first to touch the high-order groups
+#pragma unroll
+                for (int gi = S - 5; gi >= 0; --gi)
+                  if (gi >= a && gi < waited_h) mbar_wait_b(&t_empty[gi], tile_cnt & 1, 200 + 10 * Q + gi);
+                if (a < waited_h) waited_h = a;
+              }
               const int c0 = a + 4, nb = S - c0;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
@@ -243,7 +256,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
           ++b_cnt;
           if (kb == 0 && phase == 0) I8_TS(6 + Q, tile_cnt);   // first k-block of the tile issued
         }
-        umma_commit(&t_full[MD == 2 ? 1 : phase]);
+        umma_commit(&t_full[MD >= 2 ? 1 : phase]);
       }
       I8_TS(0 + Q, tile_cnt);                  // whole tile issued
       ++tile_cnt;
@@ -637,6 +650,7 @@ template <int S, int NI>
 static int launch_i8m(Ctx* ctx, const I8Args& a, int mode, cudaStream_t st) {
   if (mode == 1) return launch_i8n<S, NI, 1>(ctx, a, st);
   if (mode == 2) return launch_i8n<S, NI, 2>(ctx, a, st);
+  if (mode == 3) return launch_i8n<S, NI, 3>(ctx, a, st);
   return launch_i8n<S, NI, 0>(ctx, a, st);
 }
 
@@ -658,7 +672,7 @@ __global__ void i8_cmp_kernel(const unsigned long long* __restrict__ x, const un
 template <int S>
 static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   // BOSIP_B200_I8_MODE selects the MMA schedule (development A/B switch; all three give bit-identical results): 0 plain, 1 phased,
-  // 2 split last k-block.  The phased kernel is 23 % SLOWER on B200 at C3 (profiles/r02_phased_ab.json: 3.94 vs 3.20 ms per launch --
+  // 2 split last k-block.  The phased kernel is 23 % SLOWER on B200 at C3 (profiles/r02_mma_schedule_ab.json: 3.94 vs 3.20 ms per launch --
   // phase H streams 72 KB of operands per k-block for only ~870 clk of MMA work, 85 B/clk per SM against 44 B/clk, so the TMA feed,
   // not the drain it removes, becomes the limiter).
   static const int mode = getenv("BOSIP_B200_I8_MODE") ? atoi(getenv("BOSIP_B200_I8_MODE")) : I8_DEFAULT_MODE;
