@@ -134,6 +134,12 @@ class Context:
         self._check(self.lib.bosip_b200_i8_issuers(self.h, C.byref(n)))
         return n.value
 
+    def i8_pair(self) -> int:
+        """Paired (cta_group::2) INT8 kernel: 1 in use (BOSIP_B200_I8_PAIR=1 and the bitwise self-check passed), -1 self-check failed, 0 otherwise."""
+        n = C.c_int()
+        self._check(self.lib.bosip_b200_i8_pair(self.h, C.byref(n)))
+        return n.value
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self._check(self.lib.bosip_b200_launch_count(self.h, C.byref(n)))

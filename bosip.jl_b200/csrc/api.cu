@@ -563,6 +563,13 @@ int bosip_b200_i8_issuers(bosip_b200_ctx* h, int* out) {
   return 0;
 }
 
+int bosip_b200_i8_pair(bosip_b200_ctx* h, int* out) {
+  API_LOCK(h);
+  if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");
+  *out = ctx->i8_pair;
+  return 0;
+}
+
 int bosip_b200_launch_count(bosip_b200_ctx* h, int64_t* out) {
   API_LOCK(h);
   if (!out) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "null output");

@@ -65,6 +65,9 @@ struct Gp {
   size_t i8_b_per_out = 0;
   uint8_t* LinvI8 = nullptr;  // [p][sets][S][64 x 128 B]  byte slices of alpha_j^2 L_j^{-1} (SWIZZLE_128B tile images)
   double* cscale = nullptr;   // [p][T64*64]               2^(f_n - 13): row scale of the fixed-point representation
+  double* i8_qscale = nullptr;   // [p]         value of one unit of the integer row sums (inside the cscale allocation)
+  uint32_t* i8_nib = nullptr;    // [p][T64*8]  f_n - f_base, four bits per row (inside the cscale allocation)
+  uint8_t* LinvI8P = nullptr; // [p][sets][2][S x 8 KB]    the same slices as the per-rank operand images of the paired (cta_group::2) kernel
 };
 
 struct Timing {
@@ -84,6 +87,7 @@ struct Ctx {
   int64_t user_chunk = 0;
   int var_engine = 0, var_slices = 7;  // BOSIP_B200_VAR_*: which kernel computes ||L^-1 k*||^2
   int i8_issuers = 0;                  // MMA-issuing threads of the INT8 engine: 0 = self-check pending, else 1 or 2 (vargemm_i8.cu)
+  int i8_pair = 0;                     // paired (cta_group::2) INT8 kernel: 0 = self-check pending, 1 = in use, -1 = not used
   // chunk workspace (grown on demand)
   size_t ws_bytes = 0;
   char* ws = nullptr;

@@ -387,7 +387,7 @@ __global__ void unpad_kernel(const double* __restrict__ Pp, int P2, int N, doubl
 void gp_destroy(Gp* gp) {
   if (!gp) return;
   cudaFree(gp->block);   // Us, scale, As, LinvT, L, Linv, a live in one allocation
-  cudaFree(gp->LinvI8); cudaFree(gp->cscale);
+  cudaFree(gp->LinvI8); cudaFree(gp->LinvI8P); cudaFree(gp->cscale);
   delete gp;
 }
 

@@ -154,6 +154,10 @@ int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
  * tcgen05.mma per issuing thread only); 1 after a mismatch or with BOSIP_B200_I8_ISSUERS=1; 0 = not decided yet (no INT8 launch
  * so far). */
 int bosip_b200_i8_issuers(bosip_b200_ctx* ctx, int* out);
+/* State of the paired (tcgen05 cta_group::2, two SMs per MMA stream) INT8 kernel of this context: 1 = in use (opt-in with
+ * BOSIP_B200_I8_PAIR=1, slices = 7, after the same bitwise self-check against the single-issuer kernel), -1 = self-check failed,
+ * 0 = not requested / not decided yet.  Same results bit for bit; measured slower than the unpaired kernel on B200. */
+int bosip_b200_i8_pair(bosip_b200_ctx* ctx, int* out);
 /* ---- AMIS importance sampler, inner loop (src/samplers/amis/amis_method.jl:26-83,126-134;
  *      src/samplers/amis/proposal_distributions/normal.jl:75-100; src/sampling.jl:55-57).  The samples, log_P, Delta and
  *      log_Omega can stay in HBM between iterations (mem = BOSIP_B200_DEVICE); log_pi(xs) is bosip_b200_posterior_eval. ---- */

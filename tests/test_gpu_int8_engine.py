@@ -193,6 +193,35 @@ def test_mma_schedules_are_bit_identical(bb, ctx, engine, tmp_path, slices):
     assert all(np.array_equal(outs[0], o) for o in outs[1:])
 
 
+def test_paired_kernel_is_bit_identical(bb, ctx, engine, tmp_path):
+    """The paired INT8 kernel (tcgen05 cta_group::2: two CTAs of a cluster share one M = 256 MMA stream, per-rank operand images, relay
+    and multicast barriers; opt-in, BOSIP_B200_I8_PAIR=1) must give the same bits as the unpaired kernel: odd and even numbers of query
+    tiles, a ragged last n-tile, tiles of one to several k-blocks.  The switch is read at first use, hence the subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    outs = {}
+    for pair in (0, 1):
+        for M in (3001, 1100):          # 24 and 9 query tiles
+            out = tmp_path / f"var_p{pair}_{M}.npy"
+            code = (
+                "import sys, numpy as np\n"
+                f"sys.path.insert(0, {repr(root)})\n"
+                "import bosip_b200 as bb\n"
+                "ctx = bb.Context(0); ctx.set_variance_engine('int8', 7)\n"
+                "pr = bb.synth.make_problem('X', d=4, p=2, N=715, seed=77)\n"
+                "model = bb.GaussianProcess(pr.kernel_id, pr.lam, pr.alpha, pr.sigma)\n"
+                f"Xq = np.random.default_rng(5).uniform(pr.lb[:, None], pr.ub[:, None], size=(pr.d, {M}))\n"
+                "post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx)\n"
+                "v1 = post.mean_and_var(Xq)[1]; v2 = post.mean_and_var(Xq)[1]\n"      # first call: self-check launch, second: the kernel alone
+                f"assert np.array_equal(v1, v2); np.save({repr(str(out))}, v2); assert ctx.i8_pair() == {pair}\n")
+            subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, BOSIP_B200_I8_PAIR=str(pair)), timeout=300)
+            outs[(pair, M)] = np.load(out)
+    for M in (3001, 1100):
+        assert np.array_equal(outs[(0, M)], outs[(1, M)])
+
+
 @pytest.mark.parametrize("d,p,N,M,kernel_id", [(10, 1, 4096, 1500, 2), (4, 2, 2000, 1000, 1), (3, 3, 1025, 700, 0)])
 def test_int8_large_training_sets(bb, ctx, engine, d, p, N, M, kernel_id):
     """Deep contractions (BASELINE config 5: N = 4096, d = 10) and sizes just past a tile edge: many k-blocks per n-tile, several
