@@ -25,7 +25,7 @@
 namespace bosip {
 
 constexpr int NB = 64;
-constexpr size_t POTRF_SMEM = 2 * NB * (NB + 1) * sizeof(double);
+constexpr size_t POTRF_SMEM = NB * (NB + 1) * sizeof(double);
 
 // ------------------------------------------------------------------------------------------------ generic GEMM
 // C(m,n) = beta*C(m,n) + alpha * sum_k A(m,k) B(k,n), two-level batch (z = z1 + nb1*z2).  A and C are column-major (unit row
@@ -191,26 +191,35 @@ __global__ void pad_L_kernel(const double* __restrict__ Lin, int N, int P2, doub
 }
 
 // Factorise the 64x64 diagonal block b in place (lower), zero its strict upper part, and write its inverse into the
-// same block of Xp.  One CTA of 256 threads per output; both halves are right-looking rank-1 sweeps over shared memory with the
-// trailing region spread over all threads (two barriers per column).  flag[0] = 1 + block index on a non-positive pivot.
+// same block of Xp.  One CTA of 256 threads per output.  Thread (tr, tq) = (tid & 63, tid >> 6) keeps the 16 elements
+// (tr, tq + 4 i) of its row in REGISTERS for the whole sweep; what a column step needs from other threads -- the pivot column,
+// resp. the finished row of the inverse -- goes through a double-buffered 64-entry line in shared memory, so a step is ONE barrier,
+// 17 broadcast loads and up to 16 independent FMAs (the first version kept the block in shared memory with a read-modify-write loop
+// of variable length and two barriers per column: ~1000 clk per column, 65 us per block -- 4.2 of the 8.9 ms of an N = 4096
+// Cholesky; same operations in the same order, so L and L^-1 are bit-identical to it).  flag[0] = 1 + block index on a bad pivot.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap, double* __restrict__ Xp, int P2, int b,
                                                          int do_factor, int* __restrict__ flag, const double* __restrict__ piv_floor) {
   extern __shared__ __align__(16) unsigned char potrf_smem[];
-  double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
-  double (*x)[NB + 1] = s + NB;
-  __shared__ double diag[NB];
+  double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);   // the finished factor (for the inverse sweep)
+  __shared__ double line[2][NB];
+  __shared__ double rdiag[NB];
   const int j = blockIdx.x, tid = threadIdx.x, tr = tid & 63, tq = tid >> 6;
   double* A = Ap + (size_t)j * P2 * P2 + (size_t)b * NB + (size_t)b * NB * P2;
-  for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; s[rr][cc] = A[rr + (size_t)cc * P2]; }
-  __syncthreads();
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = A[tr + (size_t)(tq + 4 * i) * P2];
+  bool ok = true;
   if (do_factor) {
-    bool ok = true;
     // "not positive definite" = a pivot at or below rounding level of the original diagonal K_cc = alpha^2 + sigma^2 + jitter
     // (LAPACK / Julia's cholesky test `<= 0`, which for an exactly singular K is decided by rounding noise; the floor makes the
     // PosDefException deterministic and never fires for a noise variance above 1e-14 of the prior variance)
     const double floor_j = piv_floor ? piv_floor[j] : 0.0;
+    if (tq == 0) line[0][tr] = a[0];
+    __syncthreads();
+#pragma unroll
     for (int c = 0; c < NB; ++c) {
-      const double piv = s[c][c];
+      const double* col = line[c & 1];            // column c as the previous steps left it: rows >= c are final
+      const double piv = col[c];
       if (!(piv > floor_j)) { if (tid == 0) atomicCAS(flag, 0, 1 + b); ok = false; break; }  // uniform: every thread reads the same pivot
       // sqrt and reciprocal from ONE Goldschmidt iteration (hardware rsqrt seed, two coupled steps, residual correction: <= 2 ulp,
       // fastmath.cuh) instead of the library's sqrt + divide, which put ~800 dependent cycles into each of the 64 serial steps
@@ -223,44 +232,52 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ Ap
       gg = fma(gg, rr_, gg); hh = fma(hh, rr_, hh);
       const double lcc = fma(fma(-gg, gg, piv), hh, gg);          // sqrt(piv)
       const double rinv = 2.0 * fma(hh, fma(-2.0 * hh, lcc, 1.0), hh);   // 1 / lcc: one Newton step on 2 h
-      if (tid == c) diag[c] = lcc;
-      if (tq == 0 && tr > c) s[tr][c] = s[tr][c] * rinv;            // column c of L (the pivot itself stays in place until the write-back)
-      __syncthreads();
-      // rank-1 update of the trailing lower triangle: row tr, columns c+1+tq, c+5+tq, ... <= tr
-      if (tr > c) {
-        const double l_rc = s[tr][c];
-        for (int cc = c + 1 + tq; cc <= tr; cc += 4) s[tr][cc] -= l_rc * s[cc][c];
+      const double l_rc = col[tr] * rinv;                           // L[tr][c] for tr > c
+      if (tq == (c & 3)) a[c >> 2] = tr > c ? l_rc : (tr == c ? lcc : 0.0);
+      // rank-1 update of the trailing lower triangle: this thread's columns cc = tq + 4 i with c < cc <= tr
+#pragma unroll
+      for (int i = (c >> 2); i < 16; ++i) {
+        const int cc = tq + 4 * i;
+        if (cc > c && cc <= tr) a[i] -= l_rc * (col[cc] * rinv);
       }
-      __syncthreads();
+      if (c + 1 < NB) {
+        if (tq == ((c + 1) & 3) && tr >= c + 1) line[(c + 1) & 1][tr] = a[(c + 1) >> 2];
+        __syncthreads();
+      }
     }
     if (ok) {
-      for (int e = tid; e < NB * NB; e += 256) {
-        const int rr = e & 63, cc = e >> 6;
-        A[rr + (size_t)cc * P2] = cc < rr ? s[rr][cc] : (cc == rr ? diag[rr] : 0.0);
-      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const int cc = tq + 4 * i; A[tr + (size_t)cc * P2] = cc <= tr ? a[i] : 0.0; }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const int cc = tq + 4 * i; s[tr][cc] = (cc == tr && !ok) ? 1.0 : a[i]; }
+  __syncthreads();
+  // inverse: solve L X = I as 64 rank-1 sweeps: X[k][:] = B[k][:] / L[k][k], then B[i][:] -= L[i][k] X[k][:] for the rows below
+  // (only columns <= k of row k are non-zero); x[i] = X[tr][tq + 4 i] in registers, row k travels through `line`
+  if (tid < NB) rdiag[tid] = 1.0 / s[tid][tid];     // the 64 reciprocals at once (exact divisions, off the serial path)
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (tq + 4 * i == tr) ? 1.0 : 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (tr == k) {
+      const double rk = rdiag[k];
+#pragma unroll
+      for (int i = 0; i <= (k >> 2); ++i) { const int cc = tq + 4 * i; if (cc <= k) x[i] = x[i] * rk; line[k & 1][cc] = cc <= k ? x[i] : 0.0; }
     }
     __syncthreads();
-    if (tid < NB) s[tid][tid] = ok ? diag[tid] : 1.0;
-    __syncthreads();
-  }
-  // inverse: solve L X = I column-block-wise as 64 rank-1 sweeps: X[k][:] = B[k][:] / L[k][k], then B[i][:] -= L[i][k] X[k][:]
-  // for the rows below (only columns <= k of row k are non-zero)
-  for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; x[rr][cc] = rr == cc ? 1.0 : 0.0; }
-  if (tid < NB) diag[tid] = 1.0 / s[tid][tid];     // the 64 reciprocals at once (exact divisions, off the serial path)
-  __syncthreads();
-  for (int k = 0; k < NB; ++k) {
-    const double rk = diag[k];
-    if (tq == 0 && tr <= k) x[k][tr] = x[k][tr] * rk;
-    __syncthreads();
-    // rows i = k+1 .. 63 (index tr), columns jj = tq, tq+4, ... <= k
     if (tr > k) {
       const double l_ik = s[tr][k];
-      for (int jj = tq; jj <= k; jj += 4) x[tr][jj] -= l_ik * x[k][jj];
+#pragma unroll
+      for (int i = 0; i <= (k >> 2); ++i) { const int cc = tq + 4 * i; if (cc <= k) x[i] -= l_ik * line[k & 1][cc]; }
     }
-    __syncthreads();
   }
   double* X = Xp + (size_t)j * P2 * P2 + (size_t)b * NB + (size_t)b * NB * P2;
-  for (int e = tid; e < NB * NB; e += 256) { const int rr = e & 63, cc = e >> 6; X[rr + (size_t)cc * P2] = cc <= rr ? x[rr][cc] : 0.0; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const int cc = tq + 4 * i; X[tr + (size_t)cc * P2] = cc <= tr ? x[i] : 0.0; }
 }
 
 // a = K^{-1} y = L^{-T} (L^{-1} y) by two blocked triangular SOLVES with the Cholesky factor itself (not through the explicit
