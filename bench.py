@@ -234,8 +234,11 @@ def secondary_block(bb, ctx, torch, peak, hbm_peak, c3_bundle):
         _, pr, model, like, prior = make_problem(name, **kw)
         ctx.set_variance_engine("auto")
         t0 = time.perf_counter(); post = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx); fit_first = time.perf_counter() - t0
-        t0 = time.perf_counter(); post2 = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx); fit_ms = 1e3 * (time.perf_counter() - t0)
-        post2.free()
+        fit_runs = []
+        for _ in range(3):      # host wall clock around the blocking call; the best of three (an allocation on a fragmented heap costs tens of ms once in a while)
+            t0 = time.perf_counter(); post2 = bb.model_posterior(model, pr.X, pr.Y, ctx=ctx); fit_runs.append(1e3 * (time.perf_counter() - t0))
+            post2.free()
+        fit_ms = min(fit_runs)
         Xd = torch.empty((M, pr.d), dtype=torch.float64, device="cuda").t()
         bb.candidates(ctx, source(pr, M), 0, M, device_out=Xd)
         outs = {k: torch.empty(M, dtype=torch.float64, device="cuda") for k in ("log_approx_post", "log_post_mean", "log_post_var")}
@@ -265,7 +268,7 @@ def secondary_block(bb, ctx, torch, peak, hbm_peak, c3_bundle):
         oi, _ = orc.maxvar_argmax(ores["log_post_var"], False)
         sub = bb.posterior_eval(post, like, prior, Xd[:, :parity_n], 4, acq=acq)
         rec = {"workload": f"{name}: d={pr.d}, p={pr.p}, N={pr.N}, M={M}", "value": M / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": reps,
-               "fit_ms": fit_ms, "fit_ms_first_call": 1e3 * fit_first, "kernels_ms_per_step": {k: v["ms"] / reps for k, v in tm.items()},
+               "fit_ms": fit_ms, "fit_ms_runs": fit_runs, "fit_ms_first_call": 1e3 * fit_first, "kernels_ms_per_step": {k: v["ms"] / reps for k, v in tm.items()},
                "roofline": roof, "argmax_global_index": int(res["best_idx"]),
                "parity": {"against": "oracle/bosip_oracle.py posterior_eval", "points": parity_n, "max_relerr": errs,
                           "argmax_index_equal": bool(sub["best_idx"] == oi), "tolerance": 1e-9,
