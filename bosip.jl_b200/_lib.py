@@ -53,6 +53,7 @@ PROTOTYPES = {
     "bosip_b200_stream_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bosip_b200_i8_issuers": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "bosip_b200_i8_pair": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "bosip_b200_get_variance_engine": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bosip_b200_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
     "bosip_b200_set_chunk": (C.c_int, [C.c_void_p, C.c_int64]),
     "bosip_b200_set_variance_engine": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -134,6 +134,14 @@ class Context:
         self._check(self.lib.bosip_b200_i8_issuers(self.h, C.byref(n)))
         return n.value
 
+    def variance_engine(self) -> dict:
+        """Current variance-engine setting: {'engine': 'fp64'|'int8'|'auto', 'slices': bytes of alpha^2 L^-1, 'kstar_slices': bytes of K*,
+        'slice_pairs': INT8 GEMMs per contraction}."""
+        e, s, a = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.bosip_b200_get_variance_engine(self.h, C.byref(e), C.byref(s), C.byref(a)))
+        S, SA = s.value, a.value
+        return {"engine": {0: "fp64", 1: "int8", 2: "auto"}[e.value], "slices": S, "kstar_slices": SA, "slice_pairs": sum(S - i for i in range(SA))}
+
     def i8_pair(self) -> int:
         """Paired (cta_group::2) INT8 kernel: 1 in use (BOSIP_B200_I8_PAIR=1 and the bitwise self-check passed), -1 self-check failed, 0 otherwise."""
         n = C.c_int()

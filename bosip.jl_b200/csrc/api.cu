@@ -210,7 +210,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   // AUTO: the INT8 engine pays off once the contraction is more than a tile deep; below that the FP64 kernel is as fast
   bool i8 = sw.need_var && (ctx->var_engine == BOSIP_B200_VAR_INT8 || (ctx->var_engine == BOSIP_B200_VAR_AUTO && gp->N >= 128));
   if (i8 && ctx->var_engine == BOSIP_B200_VAR_AUTO && ((double)gp->N * ctx->var_slices * 255.0 * 128.0 >= 2147483647.0 || gp->N >= 8192)) i8 = false;
-  const int S8 = ctx->var_slices, KB8 = (gp->N + 127) / 128;
+  const int S8 = ctx->var_slices, SA8 = ctx->var_a_slices, KB8 = (gp->N + 127) / 128;   // slices of alpha^2 L^-1 / of K*
   int nsub8 = 1;
   if (i8) {
     for (Gp* gf : sw.fits) BOSIP_TRY(i8_prepare(ctx, gf, S8, ctx->s_comp));
@@ -230,7 +230,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   // ---- chunk size
   int64_t mc;
   if (sw.need_var) {
-    const double k_bytes_per_point = i8 ? (double)p * KB8 * 128.0 * S8 : (double)p * Ns * 8.0;
+    const double k_bytes_per_point = i8 ? (double)p * KB8 * 128.0 * SA8 : (double)p * Ns * 8.0;
     const int64_t by_mem = (int64_t)(3.0e9 / k_bytes_per_point) / TILE_M * TILE_M;
     mc = std::min<int64_t>((int64_t)ctx->sms * TILE_M * 4, std::max<int64_t>(TILE_M, by_mem));
   } else {
@@ -245,7 +245,7 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   // ---- workspace carve-up (all sizes in doubles, 256-byte aligned pieces)
   size_t off = 0;
   auto carve = [&](size_t n_doubles) { size_t o = off; off += (n_doubles * 8 + 255) / 256 * 256; return o; };
-  const size_t o_Ks = sw.need_var ? carve(i8 ? (size_t)p * (mc / TILE_M) * KB8 * S8 * 2048 : (size_t)p * Ns * mc) : 0;
+  const size_t o_Ks = sw.need_var ? carve(i8 ? (size_t)p * (mc / TILE_M) * KB8 * SA8 * 2048 : (size_t)p * Ns * mc) : 0;
   const size_t o_mu_part = carve((size_t)nsplit * p * mc);
   const size_t o_q_part = sw.need_var ? carve((size_t)p * mc) : 0;
   const size_t o_q_scr = i8 ? carve((size_t)nsub8 * p * mc) : 0;
@@ -370,12 +370,12 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
     for (int f = 0; f < n_fits; ++f) {
       Gp* gf = sw.fits[f];
       t_begin(ctx, 0, sc);
-      BOSIP_TRY(launch_kstar(ctx, gf, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var ? (i8 ? 2 : 1) : 0, S8, sc));
+      BOSIP_TRY(launch_kstar(ctx, gf, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var ? (i8 ? 2 : 1) : 0, SA8, sc));
       t_end(ctx, sc);
       if (sw.need_var) {
         t_begin(ctx, 1, sc);
         if (i8) {
-          BOSIP_TRY(launch_vargemm_i8(ctx, gf, reinterpret_cast<const uint8_t*>(Ks), mc, m_tiles, D(o_q_scr), q_part, sc));
+          BOSIP_TRY(launch_vargemm_i8(ctx, gf, reinterpret_cast<const uint8_t*>(Ks), SA8, mc, m_tiles, D(o_q_scr), q_part, sc));
           ctx->launches += 1;
         } else {
           BOSIP_TRY(launch_vargemm(ctx, gf, Ks, mc, m_tiles, q_part, sc));
@@ -581,9 +581,18 @@ int bosip_b200_set_variance_engine(bosip_b200_ctx* h, int engine, int slices) {
   API_LOCK(h);
   if (engine != BOSIP_B200_VAR_FP64 && engine != BOSIP_B200_VAR_INT8 && engine != BOSIP_B200_VAR_AUTO)
     BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "unknown variance engine");
-  if (slices == 0) slices = 7;
+  int a_slices = slices;
+  if (slices == 0) { slices = 7; a_slices = 6; }   // default: 7 slices of alpha^2 L^-1 against 6 of K* (27 slice pairs)
   if (slices < 6 || slices > 8) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "slices must be 6, 7 or 8 (0 = default)");
-  ctx->var_engine = engine; ctx->var_slices = slices;
+  ctx->var_engine = engine; ctx->var_slices = slices; ctx->var_a_slices = a_slices;
+  return 0;
+}
+
+int bosip_b200_get_variance_engine(bosip_b200_ctx* h, int* engine, int* slices, int* kstar_slices) {
+  API_LOCK(h);
+  if (engine) *engine = ctx->var_engine;
+  if (slices) *slices = ctx->var_slices;
+  if (kstar_slices) *kstar_slices = ctx->var_a_slices;
   return 0;
 }
 

@@ -86,6 +86,12 @@ struct Ctx {
   cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr, ev_dep = nullptr;
   int64_t user_chunk = 0;
   int var_engine = 0, var_slices = 7;  // BOSIP_B200_VAR_*: which kernel computes ||L^-1 k*||^2
+  // INT8 engine: byte slices of K* (var_slices = slices of alpha^2 L^-1).  Default 6 against 7: K* in 2^-47 fixed point.  Its lowest byte
+  // of a 7-byte K* meets only the MOST significant byte of L^-1 (pairs with a + b >= 7 are dropped anyway), which is small for all but a
+  // row's largest entries, so leaving that one slice pair out (27 instead of 28 INT8 GEMMs, one operand tile in seven never written, fetched
+  // or multiplied) costs 2-8 x the slicing error of the symmetric 7 x 7 scheme and stays 25 x below the 1e-10 gate
+  // (tests/test_int8_model.py, tests/test_gpu_int8_engine.py).  An explicit `slices` request (6, 7, 8) selects the symmetric scheme.
+  int var_a_slices = 6;
   int i8_issuers = 0;                  // MMA-issuing threads of the INT8 engine: 0 = self-check pending, else 1 or 2 (vargemm_i8.cu)
   int i8_pair = 0;                     // paired (cta_group::2) INT8 kernel: 0 = self-check pending, 1 = in use, -1 = not used
   // chunk workspace (grown on demand)
@@ -176,7 +182,7 @@ int launch_vargemm(Ctx* ctx, const Gp* gp, const double* Ks, int64_t mc, int64_t
 // vargemm_i8.cu
 int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st);
 int i8_nsub(const Gp* gp);
-int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int64_t mc, int64_t m_tiles, double* q_part, double* q,
+int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int a_slices, int64_t mc, int64_t m_tiles, double* q_part, double* q,
                       cudaStream_t st);
 int i8_peak(Ctx* ctx, double* burst, double* sustained);
 // epilogue.cu

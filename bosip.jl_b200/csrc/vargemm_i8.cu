@@ -210,7 +210,7 @@ struct I8Args {
 // MD = 3 additionally splits the FIRST k-block: all #1 MMAs of the new tile need the low-order groups only (which the epilogue
 // releases first), the #2 MMAs -- the only ones that touch the high-order groups -- go to the end of the k-block.
 // MD: 0 = plain, 1 = phased, 2 = split last k-block, 3 = split first and last k-block.
-template <int S, int Q, int NI, int MD>
+template <int S, int Q, int NI, int MD, int SA>
 __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_t sB_u, uint32_t tmem, uint64_t* a_full, uint64_t* a_empty,
                                          uint64_t* b_full, uint64_t* b_empty, uint64_t* t_full, uint64_t* t_empty) {
   using Cfg = I8Cfg<S>;
@@ -241,7 +241,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
           const bool split = (MD >= 2) && (kb == nkb - 1 || (MD == 3 && kb == 0));
           uint32_t hold_as[S], hold_lo[S];                      // ring slot / descriptor of the rows whose #2 MMA is deferred
 #pragma unroll
-          for (int a = S - 1; a >= 0; --a) {
+          for (int a = SA - 1; a >= 0; --a) {   // A slices 0 .. SA-1 exist (SA < S: the low-order slices of K* are not formed at all)
             if (Cfg::owner(a, NI) != Q) continue;
             if (PH && phase == 1 && a >= S - 4) continue;     // rows without a second MMA
             // slice a meets groups a .. S-1.  The epilogue hands every group back zeroed, so all MMAs accumulate and the next
@@ -308,7 +308,7 @@ __device__ __forceinline__ void i8_issue(const I8Args& g, uint32_t sA_u, uint32_
   }
 }
 
-template <int S, int NI, int MD>
+template <int S, int NI, int MD, int SA>
 __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args g) {
   constexpr bool PH = (MD == 1);
   using Cfg = I8Cfg<S>;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
       uint32_t a_cnt[2] = {0, 0}, b_cnt = 0;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const int sub = item % g.nsub, grp = item / g.nsub, mt = grp % g.m_tiles, j = grp / g.m_tiles;
-        const uint8_t* Aj = g.A + ((size_t)j * g.mtA + mt) * g.KB * S * I8_A_TILE;
+        const uint8_t* Aj = g.A + ((size_t)j * g.mtA + mt) * g.KB * SA * I8_A_TILE;
         const uint8_t* Bj = g.B + (size_t)j * g.b_per_out;
         for (int t = g.T64 - 1; t >= 0; --t) {
           if (i8_subset(t, g.T64, g.nsub) != sub) continue;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
             // phase H of the phased kernel needs B positions 4 .. S-1 and A slices S-5 .. 0 only
             const uint32_t b_off = (PH && phase == 1) ? 4u * I8_B_TILE : 0u;
             const uint32_t b_bytes = (PH && phase == 1) ? (uint32_t)(S - 4) * I8_B_TILE : (uint32_t)Cfg::B_SET;
-            const int a_top = (PH && phase == 1) ? S - 5 : S - 1;
+            const int a_top = (PH && phase == 1) ? S - 5 : SA - 1;
             for (int kb = 0; kb < nkb; ++kb) {
               const uint32_t bs = b_cnt & 1;
               mbar_wait_b(&b_empty[bs], ((b_cnt >> 1) & 1) ^ 1, 1);
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
               bulk_g2s(sB + (size_t)bs * Cfg::B_SET + b_off, Bt + (size_t)kb * Cfg::B_SET + b_off, b_bytes, &b_full[bs]);
 #endif
               ++b_cnt;
-              const uint8_t* Ak = Aj + (size_t)kb * S * I8_A_TILE;
+              const uint8_t* Ak = Aj + (size_t)kb * SA * I8_A_TILE;
 #pragma unroll 1
               for (int a = a_top; a >= 0; --a) {  // least significant slice first: it only touches the accumulators the epilogue frees first
                 const int q = Cfg::owner(a, NI);
@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) vargemm_i8_kernel(const I8Args 
   } else if (warp == 1 || warp == 10) {
     // ================================================================ MMA issuers (one thread each, disjoint slice rows)
     if (lane == 0) {
-      if (warp == 1) i8_issue<S, 0, NI, MD>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
-      else if (NI > 1) i8_issue<S, 1, NI, MD>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      if (warp == 1) i8_issue<S, 0, NI, MD, SA>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
+      else if (NI > 1) i8_issue<S, 1, NI, MD, SA>(g, smem_u32(sA), smem_u32(sB), tmem, a_full, a_empty, b_full, b_empty, t_full, t_empty);
     }
   } else {
     // ================================================================ epilogue: 8 warps, thread = (row, 32-column half)
@@ -1117,11 +1117,11 @@ static void i8_profile_dump(cudaStream_t st) {
 }
 #endif
 
-template <int S, int NI, int MD>
+template <int S, int NI, int MD, int SA = S>
 static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   const int grid = a.n_items < ctx->sms ? a.n_items : ctx->sms;
-  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
-  vargemm_i8_kernel<S, NI, MD><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
+  BOSIP_CUDA(ctx, cudaFuncSetAttribute(vargemm_i8_kernel<S, NI, MD, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8Cfg<S>::SMEM));
+  vargemm_i8_kernel<S, NI, MD, SA><<<grid, I8_THREADS, I8Cfg<S>::SMEM, st>>>(a);
   BOSIP_CUDA(ctx, cudaGetLastError());
 #ifdef BOSIP_I8_PROFILE
   i8_profile_dump(st);
@@ -1129,12 +1129,14 @@ static int launch_i8n(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   return 0;
 }
 
-template <int S, int NI>
+template <int S, int NI, int SA = S>
 static int launch_i8m(Ctx* ctx, const I8Args& a, int mode, cudaStream_t st) {
-  if (mode == 1) return launch_i8n<S, NI, 1>(ctx, a, st);
-  if (mode == 2) return launch_i8n<S, NI, 2>(ctx, a, st);
-  if (mode == 3) return launch_i8n<S, NI, 3>(ctx, a, st);
-  return launch_i8n<S, NI, 0>(ctx, a, st);
+  if (SA == S) {   // the alternative schedules are development switches of the symmetric slicings only
+    if (mode == 1) return launch_i8n<S, NI, 1, S>(ctx, a, st);
+    if (mode == 2) return launch_i8n<S, NI, 2, S>(ctx, a, st);
+    if (mode == 3) return launch_i8n<S, NI, 3, S>(ctx, a, st);
+  }
+  return launch_i8n<S, NI, 0, SA>(ctx, a, st);
 }
 
 // bitwise comparison of the rows the GEMM wrote: part[(u * p + j) * mc + r], r < rows
@@ -1177,11 +1179,11 @@ static int launch_i8_pair(Ctx* ctx, const I8Args& a0, cudaStream_t st) {
   return 0;
 }
 
-template <int S>
+template <int S, int SA = S>
 static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
   // S = 7: the paired kernel (cta_group::2), after it has reproduced the single-issuer unpaired kernel bit for bit on this context's
   // first real launch (same self-check as for the two issuing threads below; on a mismatch the context stays unpaired)
-  if (S == 7 && a.Bp != nullptr && ctx->i8_pair >= 0) {
+  if (S == 7 && SA == S && a.Bp != nullptr && ctx->i8_pair >= 0) {
     if (ctx->i8_pair == 0) {
       const size_t n = (size_t)a.nsub * a.p * (size_t)a.mc;
       double* ref = nullptr;
@@ -1229,8 +1231,8 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       unsigned int* d_mis = reinterpret_cast<unsigned int*>(ref + n);
       BOSIP_CUDA(ctx, cudaMemsetAsync(d_mis, 0, 8, st));
       I8Args b = a; b.q_part = ref;
-      BOSIP_TRY((launch_i8n<S, 1, 0>(ctx, b, st)));                // the reference: one issuer, plain schedule
-      BOSIP_TRY((launch_i8m<S, I8_ISSUERS>(ctx, a, mode, st)));
+      BOSIP_TRY((launch_i8n<S, 1, 0, SA>(ctx, b, st)));            // the reference: one issuer, plain schedule
+      BOSIP_TRY((launch_i8m<S, I8_ISSUERS, SA>(ctx, a, mode, st)));
       i8_cmp_kernel<<<ctx->sms * 4, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(ref), reinterpret_cast<const unsigned long long*>(a.q_part),
                                                    a.mc, (long long)a.m_tiles * I8_BM, a.nsub * a.p, d_mis);
       BOSIP_CUDA(ctx, cudaGetLastError());
@@ -1249,20 +1251,26 @@ static int launch_i8(Ctx* ctx, const I8Args& a, cudaStream_t st) {
       return 0;
     }
   }
-  return ctx->i8_issuers == 1 ? launch_i8m<S, 1>(ctx, a, mode, st) : launch_i8m<S, I8_ISSUERS>(ctx, a, mode, st);
+  return ctx->i8_issuers == 1 ? launch_i8m<S, 1, SA>(ctx, a, mode, st) : launch_i8m<S, I8_ISSUERS, SA>(ctx, a, mode, st);
 }
 
 // Ks8: [p][mc/128][KB][S][16 KB]; q_part: [nsub][p][mc] scratch; q: [p][mc]
-int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int64_t mc, int64_t m_tiles, double* q_part, double* q, cudaStream_t st) {
+// a_slices: byte slices of K* the cross-kernel wrote (= gp->i8_S, or 6 with 7 slices of L^-1: the default, see common.cuh)
+int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int a_slices, int64_t mc, int64_t m_tiles, double* q_part, double* q, cudaStream_t st) {
   I8Args a;
   a.A = Ks8; a.B = gp->LinvI8; a.Bp = i8_pair_enabled() ? gp->LinvI8P : nullptr; a.m_pairs = 0; a.cs = gp->cscale; a.nib = gp->i8_nib; a.qscale = gp->i8_qscale; a.q_part = q_part; a.mc = mc; a.b_per_out = gp->i8_b_per_out;
   a.KB = (gp->N + I8_BK - 1) / I8_BK; a.T64 = gp->i8_T64; a.mtA = (int)(mc / I8_BM); a.m_tiles = (int)m_tiles; a.p = gp->p;
   a.N = gp->N; a.nsub = i8_nsub(gp); a.n_items = (int)(m_tiles * gp->p * a.nsub);
-  switch (gp->i8_S) {
-    case 6: BOSIP_TRY(launch_i8<6>(ctx, a, st)); break;
-    case 7: BOSIP_TRY(launch_i8<7>(ctx, a, st)); break;
-    case 8: BOSIP_TRY(launch_i8<8>(ctx, a, st)); break;
-    default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine not prepared");
+  if (gp->i8_S == 7 && a_slices == 6) {
+    BOSIP_TRY((launch_i8<7, 6>(ctx, a, st)));
+  } else {
+    if (a_slices != gp->i8_S) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine: unsupported slice combination");
+    switch (gp->i8_S) {
+      case 6: BOSIP_TRY(launch_i8<6>(ctx, a, st)); break;
+      case 7: BOSIP_TRY(launch_i8<7>(ctx, a, st)); break;
+      case 8: BOSIP_TRY(launch_i8<8>(ctx, a, st)); break;
+      default: BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "INT8 variance engine not prepared");
+    }
   }
   const size_t n = (size_t)gp->p * mc;
   i8_qsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q_part, a.nsub, n, q);

@@ -141,14 +141,18 @@ int bosip_b200_set_chunk(bosip_b200_ctx* ctx, int64_t max_points_per_chunk);
  * (src/likelihoods/normal.jl:37,43,60,68):
  *   BOSIP_B200_VAR_FP64  mma.sync FP64 tensor cores (DMMA), plain Float64 arithmetic;
  *   BOSIP_B200_VAR_INT8  tcgen05 INT8 tensor cores on error-free byte slices of both operands (Ozaki splitting):
- *                        `slices` bytes of fixed point per operand (6, 7 or 8; 0 = 7, i.e. 2^-56 of the row scale),
- *                        integer products exact, one FP64 rounding per Horner step in the epilogue.
+ *                        `slices` bytes of fixed point per operand (6, 7 or 8: S (S + 1) / 2 exact INT8 GEMMs), or 0 = the
+ *                        default: 7 bytes of alpha^2 L^-1 (2^-56 of the row scale) against 6 bytes of the cross-kernel
+ *                        values (2^-48), 27 INT8 GEMMs -- the 28th slice pair of the 7 x 7 scheme only meets the most
+ *                        significant byte of L^-1; integer products exact, rounding only in the epilogue.
  * Both satisfy the 1e-10 parity bound; results differ in the last bits.  The INT8 engine needs N < 8192 (exact integer
  * accumulation); BOSIP_B200_VAR_AUTO falls back to FP64 above that, an explicit INT8 request returns BOSIP_B200_EINVAL. */
 #define BOSIP_B200_VAR_FP64 0
 #define BOSIP_B200_VAR_INT8 1
 #define BOSIP_B200_VAR_AUTO 2 /* default: INT8 for N >= 128 training points, FP64 below */
 int bosip_b200_set_variance_engine(bosip_b200_ctx* ctx, int engine, int slices);
+/* The current setting: engine (BOSIP_B200_VAR_*), byte slices of alpha^2 L^-1 and of the cross-kernel values (any pointer may be NULL). */
+int bosip_b200_get_variance_engine(bosip_b200_ctx* ctx, int* engine, int* slices, int* kstar_slices);
 /* How many threads issue tcgen05.mma in the INT8 engine of this context: 2 (default) only after a one-off self-check has
  * shown, on the first real chunk, that the two-issuer kernel reproduces the single-issuer kernel bit for bit (PTX orders
  * tcgen05.mma per issuing thread only); 1 after a mismatch or with BOSIP_B200_I8_ISSUERS=1; 0 = not decided yet (no INT8 launch

@@ -8,6 +8,8 @@ Scheme (Ozaki-style error-free splitting, base 256, S slices per operand):
     A_a = byte (S-1-a) of IA (unsigned), B_b = balanced signed digit (S-1-b) of IB, a = b = 0 most significant
     D_g = sum_{a+b=g} A_a . B_b^T  for g < S (exact int32 on the tensor cores); pairs with a + b >= S are dropped
     v[i,n] = 2^(f_n-13) * sum_g 2^-8g D_g ,   q[i] = sum_n v[i,n]^2
+Default of the library (slices = 0): S = 7 slices of alpha^2 L^-1 against SA = 6 slices of K* (IA = rn(k * 2^47)): rows a = 0 .. 5 of the
+slice-pair triangle, 27 pairs -- the 28th, (6, 0), would multiply the lowest byte of K* with the MOST significant byte of L^-1.
 """
 import math
 
@@ -49,16 +51,18 @@ def slice_b(B, f, S):
     return planes, I
 
 
-def engine_q(Kstar, B, S=7):
-    """q[i] = sum_n v[i,n]^2 as the engine computes it; also returns the int32 bound check and the exact integer dot products."""
+def engine_q(Kstar, B, S=7, SA=None):
+    """q[i] = sum_n v[i,n]^2 as the engine computes it; also returns the int32 bound check and the exact integer dot products.
+    SA: byte slices of K* (default S; the library's default configuration is S = 7, SA = 6)."""
+    SA = S if SA is None else SA
     M, N = Kstar.shape
     f = row_exponents(B)
-    A, IA = slice_a(Kstar, S)
+    A, IA = slice_a(Kstar, SA)          # slice a carries the weight 2^(-8a-7) whatever SA is
     Bp, IB = slice_b(B, f, S)
     D = []
     for g in range(S):
         Dg = np.zeros((M, N), dtype=np.int64)
-        for a in range(g + 1):
+        for a in range(min(g + 1, SA)):
             Dg += A[a] @ Bp[g - a].T
         assert np.max(np.abs(Dg)) < 2 ** 31                            # the TMEM accumulators are int32
         D.append(Dg)

@@ -54,6 +54,18 @@ def test_slicing_scheme_error(case, S, bound):
         assert _err(q, exact, alpha ** 2) < 2 * e64 + 1e-16
 
 
+def test_default_scheme_six_kstar_slices(case):
+    """The library's default: 7 slices of alpha^2 L^-1, 6 of K* (27 slice pairs).  Leaving the pair (lowest byte of K*) x (highest byte
+    of L^-1) out costs a few times the slicing error of the 7 x 7 scheme and stays two orders of magnitude below what 6 x 6 gives."""
+    Ks, B, alpha, exact = case
+    q76, _, _ = im.engine_q(Ks, B, 7, 6)
+    q77, _, _ = im.engine_q(Ks, B, 7)
+    q66, _, _ = im.engine_q(Ks, B, 6)
+    e76, e77, e66 = (_err(q, exact, alpha ** 2) for q in (q76, q77, q66))
+    assert e76 < 6e-14                      # ~ 40 Float64 roundings of alpha^2; the parity gate on sigma^2 >= 6e-4 alpha^2 needs 6e-14
+    assert e76 < 20 * e77 + 1e-15 and e76 < e66 / 20
+
+
 def test_operand_ranges(case):
     Ks, B, alpha, _ = case
     for S in (6, 7, 8):

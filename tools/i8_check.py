@@ -13,7 +13,7 @@ from bosip_b200 import synth  # noqa: E402
 from oracle import bosip_oracle as orc  # noqa: E402
 
 
-def compare(name, M, ctx, slices_list=(7, 8, 6), seed=3, near_train=True):
+def compare(name, M, ctx, slices_list=(0, 7, 8, 6), seed=3, near_train=True):
     pr = synth.make_problem(name)
     rng = np.random.default_rng(seed)
     Xq = rng.uniform(pr.lb[:, None], pr.ub[:, None], size=(pr.d, M))
@@ -74,7 +74,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "time":
         for spec in sys.argv[2:] or ["C3"]:
             cfg, _, m = spec.partition(":")
-            timing(cfg, int(m) if m else {"C3": 148 * 128 * 8, "C2": 10 ** 6, "C5": 148 * 128 * 2}[cfg], ctx, slices_list=(7,))
+            timing(cfg, int(m) if m else {"C3": 148 * 128 * 8, "C2": 10 ** 6, "C5": 148 * 128 * 2}[cfg], ctx, slices_list=(0, 7))   # 0: default (7 x 6 slices)
         return
     print(json.dumps({"int8_peak_tops": ctx.int8_peak(), **ctx.fp64_peak()}), flush=True)
     compare("C1", 1000, ctx)
@@ -84,7 +84,7 @@ def main():
         return
     timing("C3", 148 * 128 * 8, ctx)
     timing("C2", 10 ** 6, ctx)
-    compare("C5", 2000, ctx, slices_list=(7,))
+    compare("C5", 2000, ctx, slices_list=(0, 7))
     timing("C5", 148 * 128 * 2, ctx, slices_list=(7,))
 
 
