@@ -8,8 +8,9 @@ LIB = os.path.join(ROOT, "bosip.jl_b200", "libbosip_b200.so")
 OUT = os.path.join(ROOT, "profiles")
 # output name -> (substring of the mangled name, further required substring)
 KERNELS = {
-    "vargemm_i8": ("vargemm_i8_kernelILi7ELi2E", ""),                  # default engine: S = 7 slices, two MMA issuers
-    "kstar": ("kstar_kernelILi2ELi5ELi2ELi7E", ""),                    # Matern-5/2, d = 5, INT8 slice mode, S = 7 (config C3)
+    "vargemm_i8": ("vargemm_i8_kernelILi7ELi2ELi0ELi6E", ""),          # default engine: 7 slices of alpha^2 L^-1 x 6 of K*, two MMA issuers, plain schedule
+    "kstar": ("kstar_kernelILi2ELi5ELi2ELi6E", ""),                    # Matern-5/2, d = 5, INT8 slice mode, 6 slices of K* (config C3)
+    "vargemm_i8_pair": ("vargemm_i8p_kernel", ""),                     # opt-in paired kernel (tcgen05 cta_group::2, multicast commits)
     "vargemm": ("14vargemm_kernel", ""),                               # FP64 DMMA engine
 }
 KEY = ("UTCIMMA", "UTCBAR", "UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "DMMA", "SYNCS", "DFMA", "DADD", "DMUL", "IMAD.WIDE", "PRMT", "MUFU", "F2I", "I2F",
