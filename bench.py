@@ -733,7 +733,7 @@ def main_threads(args, torch):
     clocks = sampler.stop()
     l2 = sum(mctx.context(r).launch_count() for r in range(n))
     # end to end with host candidates: pageable NumPy in, three vectors out, sharded inside the library
-    Xh = bb.synth.philox_uniform_candidates(SEED, 0, min(total, 4 * 10 ** 6), pr.lb, pr.ub)
+    Xh = bb.synth.philox_uniform_candidates(SEED, 0, min(total, 2 * 10 ** 6 * n), pr.lb, pr.ub)    # 2e6 points per device: ~26 chunks each
     outs = {k: np.empty(Xh.shape[1]) for k in ("log_approx_post", "log_post_mean", "log_post_var")}
     bb.posterior_eval_multi(mpost, like, prior, Xh, 7, acq=acq, out=outs)
     t1 = time.perf_counter()
