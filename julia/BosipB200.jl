@@ -398,11 +398,23 @@ end
 
 
 # ---- variance engine ----------------------------------------------------------------------------------------------
-"Select the kernel behind the variance half of mean_and_var: :fp64 (DMMA), :int8 (tcgen05 on error-free byte slices) or :auto."
+"""
+Select the kernel behind the variance half of mean_and_var: :fp64 (DMMA), :int8 (tcgen05 on error-free byte slices) or :auto.
+`slices = 0` is the default INT8 scheme (7 bytes of α²L⁻¹ against 6 of the cross-kernel values, 27 exact INT8 GEMMs); 6, 7, 8 select
+the symmetric schemes.
+"""
 function set_variance_engine!(engine::Symbol=:auto; slices::Integer=0)
     ctx = context()
     code = engine === :fp64 ? 0 : engine === :int8 ? 1 : 2
     check(ctx, ccall((:bosip_b200_set_variance_engine, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, code, slices))
+end
+
+"The current setting as (engine, slices of α²L⁻¹, slices of K*)."
+function variance_engine()
+    ctx = context()
+    e = Ref{Cint}(0); s = Ref{Cint}(0); a = Ref{Cint}(0)
+    check(ctx, ccall((:bosip_b200_get_variance_engine, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}, Ptr{Cint}, Ptr{Cint}), ctx.h, e, s, a))
+    return ((:fp64, :int8, :auto)[e[] + 1], Int(s[]), Int(a[]))
 end
 
 # ---- AMIS inner loop (src/samplers/amis/amis_method.jl:46-78) -------------------------------------------------------
