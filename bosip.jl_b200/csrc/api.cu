@@ -373,6 +373,10 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
       BOSIP_TRY(launch_kstar(ctx, gf, x_dev, mv, mc, m_tiles, nsplit, nspan, Ks, mu_part, sw.need_var ? (i8 ? 2 : 1) : 0, SA8, sc));
       t_end(ctx, sc);
       if (sw.need_var) {
+#ifdef BOSIP_I8_DEBUG_FILL_A   // dev build: overwrite the K* slices with a constant byte before the GEMM (energy-per-operation probe; results are garbage)
+        if (i8) { static const int fill = getenv("BOSIP_I8_FILL_A") ? atoi(getenv("BOSIP_I8_FILL_A")) : -1;
+                  if (fill >= 0) cudaMemsetAsync(Ks, fill, (size_t)p * (mc / TILE_M) * KB8 * SA8 * 16384, sc); }
+#endif
         t_begin(ctx, 1, sc);
         if (i8) {
           BOSIP_TRY(launch_vargemm_i8(ctx, gf, reinterpret_cast<const uint8_t*>(Ks), SA8, mc, m_tiles, D(o_q_scr), q_part, sc));
