@@ -219,7 +219,8 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
 
   // ---- n-split of the cross-kernel so that its shared-memory footprint allows >= 4 CTAs per SM
   // (the INT8 slice writer walks 32 training points per iteration: spans are multiples of 32)
-  static const int kstar_smem_kb = getenv("BOSIP_KSTAR_SMEM_KB") ? atoi(getenv("BOSIP_KSTAR_SMEM_KB")) : 56;  // dev A/B switch
+  static const int kstar_smem_kb = getenv("BOSIP_KSTAR_SMEM_KB") ? atoi(getenv("BOSIP_KSTAR_SMEM_KB")) : 40;  // dev A/B switch; measured per 8 / 4 / 14 launches
+  // at C3 / C5 / C2 (ms): 16 KB 6.21 / 4.17 / 1.27, 24 KB 6.28 / 4.33 / 1.29, 32 KB 6.09 / 4.41 / 1.19, 40 KB 5.93 / 4.48 / 1.09, 48 KB 6.38 / 4.53 / 1.10, 56 KB 6.42 / 4.45 / 1.24
   const int span_q = 32;  // same partition for every engine and for the mean-only path: the mean stays bit-identical across them
   int nspan = (int)((kstar_smem_kb * 1024) / (8 * (gp->dp + 1))) & ~(span_q - 1);
   nspan = std::max(span_q, std::min(nspan, (int)round_up(Ns, span_q)));
@@ -231,8 +232,10 @@ static int run_sweep(Ctx* ctx, Sweep& sw) {
   int64_t mc;
   if (sw.need_var) {
     const double k_bytes_per_point = i8 ? (double)p * KB8 * 128.0 * SA8 : (double)p * Ns * 8.0;
-    const int64_t by_mem = (int64_t)(3.0e9 / k_bytes_per_point) / TILE_M * TILE_M;
-    mc = std::min<int64_t>((int64_t)ctx->sms * TILE_M * 4, std::max<int64_t>(TILE_M, by_mem));
+    static const double ws_cap = getenv("BOSIP_CHUNK_WS_GB") ? atof(getenv("BOSIP_CHUNK_WS_GB")) * 1e9 : 3.0e9;   // dev A/B switch
+    const int64_t by_mem = (int64_t)(ws_cap / k_bytes_per_point) / TILE_M * TILE_M;
+    static const int tiles_per_sm = getenv("BOSIP_CHUNK_TILES_PER_SM") ? std::max(1, atoi(getenv("BOSIP_CHUNK_TILES_PER_SM"))) : 4;   // dev A/B switch
+    mc = std::min<int64_t>((int64_t)ctx->sms * TILE_M * tiles_per_sm, std::max<int64_t>(TILE_M, by_mem));
   } else {
     mc = (int64_t)ctx->sms * TILE_M * 16;
   }

@@ -44,8 +44,13 @@ template <int S> struct I8Cfg {
   // That race dead-locked builds with a shallow shared ring.)
   // Sized so that A rings + two B sets fill the 227 KB of shared memory: S = 6: 4 + 4, S = 7: 4 + 3, S = 8: 3 + 3 tiles of 16 KB.
   static constexpr int A_SLOTS = (S == 6) ? 8 : (S == 7) ? 7 : 6;
+#ifdef BOSIP_I8_RING_SWAP   // dev A/B: the odd slot goes to issuer 1 instead of issuer 0
+  static constexpr int ring(int q, int ni) { return ni == 1 ? A_SLOTS : (q == 0 ? A_SLOTS / 2 : (A_SLOTS + 1) / 2); }
+  static constexpr int ring_base(int q, int ni) { return (ni == 1 || q == 0) ? 0 : A_SLOTS / 2; }
+#else
   static constexpr int ring(int q, int ni) { return ni == 1 ? A_SLOTS : (q == 0 ? (A_SLOTS + 1) / 2 : A_SLOTS / 2); }
   static constexpr int ring_base(int q, int ni) { return (ni == 1 || q == 0) ? 0 : (A_SLOTS + 1) / 2; }
+#endif
   static constexpr int B_SET = S * I8_B_TILE;
   static constexpr size_t SMEM = 1024 + (size_t)A_SLOTS * I8_A_TILE + 2 * (size_t)B_SET + 256;
 };
@@ -1054,7 +1059,9 @@ int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st) {
 int i8_nsub(const Gp* gp) {
   const int T64 = (gp->N + I8_BN - 1) / I8_BN;
   static const int forced = getenv("BOSIP_I8_NSUB") ? atoi(getenv("BOSIP_I8_NSUB")) : 0;  // dev A/B switch
-  int nsub = forced > 0 ? forced : T64 / 4;
+  // measured (27-pair engine, full clock / power-capped bench): C3 (T64 = 16) nsub 1 / 2 / 3 / 4 / 8: 11.17 / 10.36 / 10.40 / 10.62 / 10.89 ms per
+  // 4 launches, bench 1.971e7 vs 1.937e7 pts/s for 2 vs 4; C5 (T64 = 64) nsub 2 / 4 / 8: 19.56 / 18.39 / 17.96 ms per 2 launches
+  int nsub = forced > 0 ? forced : T64 / 8;
   nsub = nsub < 1 ? 1 : (nsub > 8 ? 8 : nsub);
   return nsub > T64 ? T64 : nsub;
 }
