@@ -123,7 +123,8 @@ __device__ __forceinline__ const double* exp_table_lane(const double* tab) { ret
 
 // tab: the calling lane's view of the table (exp_table_lane).  CUT = false skips the underflow cut-off: only for callers whose
 // argument is bounded well below 708.
-template <int REP, bool CUT = true>
+// E2: the result is scaled by 2^E2 for free (added to the exponent patch) -- the INT8 slice writer wants k * 2^(8 SA - 1)
+template <int REP, bool CUT = true, int E2 = 0>
 __device__ __forceinline__ double fast_exp_neg_t(double s, const double* __restrict__ tab) {
   const double x = -s;
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
@@ -136,7 +137,7 @@ __device__ __forceinline__ double fast_exp_neg_t(double s, const double* __restr
   const int ni = __double2loint(t);                         // n as a two's-complement integer
   const double T = tab[(ni & (EXP_TAB_N - 1)) * REP];
   const double v0 = fma(T, p, T);
-  const int hi = __double2hiint(v0) + (int)((unsigned)(ni >> 8) << 20);
+  const int hi = __double2hiint(v0) + (int)((unsigned)((ni >> 8) + E2) << 20);
   if (!CUT) return __hiloint2double(hi, __double2loint(v0));
   // s in (708.06, +Inf] -> (almost) 0, decided on the high word in the integer pipe (negative s and NaN fall through).  Only the
   // high word is cleared: the result is a denormal below 2^-1042 rather than an exact zero, one select instead of two.
@@ -159,12 +160,12 @@ __device__ __forceinline__ double fast_sqrt1(double x) {
   return fma(d, h, g);
 }
 
-template <int KERNEL, int REP, bool CUT = true>
+template <int KERNEL, int REP, bool CUT = true, int E2 = 0>
 __device__ __forceinline__ double kernel_from_r2_t(double r2, const double* __restrict__ tab) {
-  if (KERNEL == 0) return fast_exp_neg_t<REP, CUT>(r2, tab);
+  if (KERNEL == 0) return fast_exp_neg_t<REP, CUT, E2>(r2, tab);
   const double s = fast_sqrt1(r2);
-  if (KERNEL == 1) return (1.0 + s) * fast_exp_neg_t<REP, CUT>(s, tab);
-  return (1.0 + s + r2 * (1.0 / 3.0)) * fast_exp_neg_t<REP, CUT>(s, tab);
+  if (KERNEL == 1) return (1.0 + s) * fast_exp_neg_t<REP, CUT, E2>(s, tab);
+  return (1.0 + s + r2 * (1.0 / 3.0)) * fast_exp_neg_t<REP, CUT, E2>(s, tab);
 }
 
 }  // namespace bosip

@@ -72,11 +72,18 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
   }
   __syncthreads();  // barrier init visible to all waiters
   mbar_wait(&bar, 0);
+  if constexpr (MODE == 2) {
+    // The kernel values are formed already scaled by 2^(8S-1) (the fixed-point scale of the byte slices, folded into the exponent
+    // patch of exp: one FP64 multiply per value less); the weights take the inverse power of two, so every product k * a of the
+    // mean is the same Float64 number as in the other modes (exact scalings), and the mean stays bit-identical across engines.
+    __syncthreads();
+    for (int i = tid; i < len; i += TILE_M) sa[i] *= ((S == 8) ? 0x1p-63 : (S == 7 ? 0x1p-55 : 0x1p-47));
+    __syncthreads();
+  }
 
   double acc = 0.0;
   const int row_sw = (int)(m & 3);
   if constexpr (MODE == 2) {
-    const double fx = (S == 8) ? 9223372036854775808.0 : (S == 7 ? 36028797018963968.0 : 140737488355328.0);  // 2^(8S-1)
     const int KB = (Ns + 127) >> 7;
     unsigned char* tile0 = reinterpret_cast<unsigned char*>(Ks) +
                            (((size_t)j * (size_t)(mc >> 7) + blockIdx.x) * KB) * (size_t)(S * 16384) + (tid >> 3) * 1024 + (tid & 7) * 128;
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(TILE_M) kstar_kernel(const double* __restrict_
         double kv[4];
         unsigned long long iv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2_t<KERNEL, KSTAR_EXP_REP>(r2[e], exp_tab); iv[e] = __double2ull_rn(kv[e] * fx); }
+        for (int e = 0; e < 4; ++e) { kv[e] = kernel_from_r2_t<KERNEL, KSTAR_EXP_REP, true, 8 * S - 1>(r2[e], exp_tab); iv[e] = __double2ull_rn(kv[e]); }
         const double2 a01 = *reinterpret_cast<const double2*>(sa + n + 4 * q4);
         const double2 a23 = *reinterpret_cast<const double2*>(sa + n + 4 * q4 + 2);
         acc = fma(kv[0], a01.x, acc); acc = fma(kv[1], a01.y, acc); acc = fma(kv[2], a23.x, acc); acc = fma(kv[3], a23.y, acc);
