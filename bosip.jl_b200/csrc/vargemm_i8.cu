@@ -9,6 +9,9 @@
 // precision (2^-8S relative to the row scale) and are skipped, which leaves S(S+1)/2 INT8 GEMMs.  The FP64 value
 //     v[i,n] = 2^(f_n-13) * sum_g 2^-8g D_g[i,n]
 // is assembled in the epilogue (one int64 per column for S <= 7, an FP64 Horner chain for S = 8), squared and added to the row sum.
+// Template parameter SA < S: K* carries only SA byte slices (IA = rn(k 2^(8SA-1)); slice a keeps its weight 2^(-8a-7)), rows
+// a = SA .. S-1 of the slice-pair triangle do not exist.  The library's default is S = 7, SA = 6 (27 pairs): the 28th pair would
+// multiply the lowest byte of K* with the most significant byte of alpha^2 L^{-1} only (Ctx::var_a_slices in common.cuh).
 //
 // Shape of one CTA step: query tile 128 rows (MMA M) x 64 rows of L^{-1} (n-tile) x one 128-byte k-block.  All S group
 // accumulators of the n-tile are live at once (S x 64 TMEM columns <= 512), so every operand tile is loaded exactly once per
