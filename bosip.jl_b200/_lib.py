@@ -58,6 +58,7 @@ PROTOTYPES = {
     "bosip_b200_set_chunk": (C.c_int, [C.c_void_p, C.c_int64]),
     "bosip_b200_set_variance_engine": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bosip_b200_int8_peak": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "bosip_b200_int8_peak_random": (C.c_int, [C.c_void_p, c_double_p]),
     "bosip_b200_gp_fit": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                     c_double_p, c_double_p, c_double_p, C.POINTER(GpOpts), C.POINTER(C.c_void_p)]),
     "bosip_b200_gp_load_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,

@@ -168,6 +168,13 @@ class Context:
         self._check(self.lib.bosip_b200_int8_peak(self.h, C.byref(a), C.byref(b) if sustained else None))
         return (a.value, b.value) if sustained else a.value
 
+    def int8_peak_random(self) -> float:
+        """Sustained (~2 s, power-capped) tcgen05 INT8 issue rate with pseudo-random operand bytes (TOPS): what the multipliers' operand-dependent
+        switching energy leaves of the issue-rate ceiling in a long run."""
+        a = C.c_double()
+        self._check(self.lib.bosip_b200_int8_peak_random(self.h, C.byref(a)))
+        return a.value
+
     def fp64_peak(self):
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.bosip_b200_fp64_peak(self.h, C.byref(a), C.byref(b)))

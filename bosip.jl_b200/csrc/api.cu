@@ -1029,7 +1029,14 @@ int bosip_b200_confidence_iou(bosip_b200_ctx* h, const double* log_fa, const dou
 int bosip_b200_int8_peak(bosip_b200_ctx* h, double* burst_tops, double* sustained_tops) {
   API_LOCK(h);
   if (!burst_tops) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "burst_tops must not be NULL");
-  return i8_peak(ctx, burst_tops, sustained_tops);
+  return i8_peak(ctx, burst_tops, sustained_tops, nullptr);
+}
+
+int bosip_b200_int8_peak_random(bosip_b200_ctx* h, double* sustained_tops) {
+  API_LOCK(h);
+  if (!sustained_tops) BOSIP_FAIL(ctx, BOSIP_B200_EINVAL, "sustained_tops must not be NULL");
+  double burst = 0.0;
+  return i8_peak(ctx, &burst, nullptr, sustained_tops);
 }
 
 int bosip_b200_fp64_peak(bosip_b200_ctx* h, double* dmma, double* dfma) {

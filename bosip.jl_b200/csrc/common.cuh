@@ -184,7 +184,7 @@ int i8_prepare(Ctx* ctx, Gp* gp, int S, cudaStream_t st);
 int i8_nsub(const Gp* gp);
 int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int a_slices, int64_t mc, int64_t m_tiles, double* q_part, double* q,
                       cudaStream_t st);
-int i8_peak(Ctx* ctx, double* burst, double* sustained);
+int i8_peak(Ctx* ctx, double* burst, double* sustained, double* sustained_random);
 // epilogue.cu
 int launch_epilogue(Ctx* ctx, const Gp* gp, const EpiParams& ep, const double* xq, const double* logprior,
                     const double* mean_at_xq, int64_t m_valid, int64_t mc, int nsplit, const double* mu_part,

@@ -1290,14 +1290,19 @@ int launch_vargemm_i8(Ctx* ctx, const Gp* gp, const uint8_t* Ks8, int a_slices, 
 
 // ------------------------------------------------------------------------------------------------ INT8 roofline probe
 // One CTA per SM issues `iters` x 4 tcgen05.mma (M=128, N=256, K=32) on operands that stay resident in shared memory.
-__global__ void __launch_bounds__(128) i8_peak_kernel(int iters) {
+// pattern 0: operand bytes 0..3 (few set bits); pattern 1: hashed pseudo-random bytes (what byte slices of real numbers look like)
+__global__ void __launch_bounds__(128) i8_peak_kernel(int iters, int pattern) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sA = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sB = sA + 4 * I8_A_TILE;
   __shared__ __align__(8) uint64_t done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < (4 * I8_A_TILE + 4 * 256 * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = 0x01010101u * (i & 3);
+  for (int i = tid; i < (4 * I8_A_TILE + 4 * 256 * 128) / 4; i += 128) {
+    uint32_t v = 0x01010101u * (i & 3);
+    if (pattern) { v = (uint32_t)i * 2654435761u + blockIdx.x * 40503u; v ^= v >> 15; v *= 2246822519u; v ^= v >> 13; v *= 3266489917u; v ^= v >> 16; }
+    reinterpret_cast<uint32_t*>(sA)[i] = v;
+  }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   if (tid == 0) { mbar_init(&done, 1); mbar_fence_init(); }
   if (warp == 0) {
@@ -1324,18 +1329,20 @@ __global__ void __launch_bounds__(128) i8_peak_kernel(int iters) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "n"(512));
 }
 
-int i8_peak(Ctx* ctx, double* burst, double* sustained) {
+// sustained_random (optional): the same 2 s loop with pseudo-random operand bytes -- the issue rate the part holds under its power cap
+// when the multipliers see operands like the engine's byte slices (the operand-dependent switching energy decides the clock)
+int i8_peak(Ctx* ctx, double* burst, double* sustained, double* sustained_random) {
   const size_t smem = 4 * (size_t)I8_A_TILE + 4 * 256 * 128 + 1024;
   BOSIP_CUDA(ctx, cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = ctx->s_comp;
   const int iters = 10000;  // 2.7 ms per launch
   const double ops = 2.0 * (double)ctx->sms * iters * 4.0 * 128.0 * 256.0 * 32.0;
-  i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(200);
+  i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(200, 0);
   BOSIP_CUDA(ctx, cudaStreamSynchronize(st));
   float best = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
     BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_t0, st));
-    i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(iters);
+    i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(iters, 0);
     BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_t1, st));
     BOSIP_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
     float ms = 0;
@@ -1343,17 +1350,19 @@ int i8_peak(Ctx* ctx, double* burst, double* sustained) {
     if (ms < best) best = ms;
   }
   *burst = ops / (best * 1e-3) / 1e12;
-  if (sustained) {  // back to back for ~2 s: what the part holds under its power cap; the rate of the last quarter is reported
+  for (int pattern = 0; pattern < 2; ++pattern) {  // back to back for ~2 s: what the part holds under its power cap; the rate of the last quarter is reported
+    double* out = pattern ? sustained_random : sustained;
+    if (!out) continue;
     const int launches = 800, tail = 200;
     for (int l = 0; l < launches; ++l) {
       if (l == launches - tail) BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_t0, st));
-      i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(iters);
+      i8_peak_kernel<<<ctx->sms, 128, smem, st>>>(iters, pattern);
     }
     BOSIP_CUDA(ctx, cudaEventRecord(ctx->ev_t1, st));
     BOSIP_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
     float ms = 0;
     BOSIP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
-    *sustained = ops * tail / (ms * 1e-3) / 1e12;
+    *out = ops * tail / (ms * 1e-3) / 1e12;
   }
   return 0;
 }

@@ -192,6 +192,10 @@ int bosip_b200_resample(bosip_b200_ctx* ctx, int d, const double* X, const doubl
  * in TOPS counting 2 ops per multiply-accumulate: the roofline denominator of the INT8 engine.  burst = best of five 2.7 ms
  * launches; sustained (optional, may be NULL; takes ~2 s) = the rate the part holds under its power cap. */
 int bosip_b200_int8_peak(bosip_b200_ctx* ctx, double* burst_tops, double* sustained_tops);
+/* The same sustained loop (~2 s) with pseudo-random operand bytes instead of near-zero ones: the issue rate the part holds under
+ * its power cap when the INT8 multipliers see operands like the engine's byte slices.  Context for the roofline fraction: the
+ * switching energy of the multipliers depends on the operand bits, and in long runs it, not the schedule, sets the clock. */
+int bosip_b200_int8_peak_random(bosip_b200_ctx* ctx, double* sustained_tops);
 
 /* ---- GP conditioning: replaces BOSS.model_posterior(bosip.problem)
  *      (src/posterior/log_posterior.jl:81,115,148,182,214) --------------------------------------------- */
