@@ -119,6 +119,9 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
 // same, from the low descriptor words (the high word -- 1024-byte group stride, version 1, SWIZZLE_128B -- is a constant)
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | 0x10000u; }
 __device__ __forceinline__ void umma_i8_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+#ifdef BOSIP_I8_DEBUG_NOMMA   // energy probe: the whole operand stream without the multiplications (results are garbage)
+  return;
+#endif
   asm volatile(
       "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, 1, 0;\nmov.b64 da, {%1, %4};\nmov.b64 db, {%2, %4};\n"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n}\n"
