@@ -125,6 +125,46 @@ def test_auto_engine_and_option_errors(bb, ctx, engine):
     assert ctx.int8_peak() > 1000.0                      # TOPS; the tcgen05 path is alive
 
 
+def test_int8_maximum_training_set_size(bb, ctx, engine):
+    """The INT8 engine's exact integer accumulation holds for N < 8192 (int32 group sums, the int64 assembly): the largest supported
+    size against the oracle (default 7 x 6 slicing and the symmetric 7 x 7 one), and the limit itself -- N = 8192 is refused on an
+    explicit INT8 request and falls back to the FP64 engine under `auto`."""
+    d, p, N, M = 6, 1, 8191, 300
+    rng = np.random.default_rng(8191)
+    X = rng.uniform(-5, 5, (d, N)); Y = np.sin(X).sum(axis=0)[None, :] + 0.05 * rng.standard_normal((p, N))
+    lam = rng.uniform(1.5, 4, (d, p)); alpha = np.array([1.3]); sigma = 0.05 * alpha
+    Xq = rng.uniform(-5, 5, (d, M)); Xq[:, :16] = X[:, :16]
+    model = bb.GaussianProcess(2, lam, alpha, sigma)
+    post = bb.model_posterior(model, X, Y, ctx=ctx)
+    ofit = orc.gp_fit(2, X, Y, lam, alpha, sigma)
+    omu, ovar = orc.gp_predict(ofit, Xq)
+    kxx = alpha ** 2
+    engine("fp64")
+    _, var64 = post.mean_and_var(Xq)
+    for slices in (0, 7):
+        engine("int8", slices)
+        mu, var = post.mean_and_var(Xq)
+        assert _var_err(var, ovar, kxx) < TOL and _var_err(var, var64, kxx) < TOL
+        assert _var_err(var, ovar, kxx) < 10 * _var_err(var64, ovar, kxx) + 5e-12
+        assert np.max(np.abs(mu - omu)) <= 1e-9 * np.max(np.abs(ofit.a)) * N      # a cancelling sum of N terms, see the test above
+    post.free()
+    # the limit
+    N2 = 8192
+    X2 = rng.uniform(-5, 5, (2, N2)); Y2 = np.sin(X2).sum(axis=0)[None, :]
+    model2 = bb.GaussianProcess(2, np.full((2, 1), 2.0), np.array([1.0]), np.array([0.05]))
+    post2 = bb.model_posterior(model2, X2, Y2, ctx=ctx)
+    Xq2 = rng.uniform(-5, 5, (2, 130))
+    engine("int8", 0)
+    with pytest.raises(bb.BosipB200Error):
+        post2.mean_and_var(Xq2)
+    engine("auto")
+    _, va = post2.mean_and_var(Xq2)
+    engine("fp64")
+    _, vf = post2.mean_and_var(Xq2)
+    assert np.array_equal(va, vf)
+    post2.free()
+
+
 def test_int8_bi_ensemble_matches_fp64(bb, ctx, engine):
     pr = bb.synth.make_problem("C2")
     rng = np.random.default_rng(3)
